@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""bench.py -- Mrays/s and ms/frame of the voxel-rt per-pixel path on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3ii_4k|C2_1080p|C3i_4k|C3ii_pitched_4k|C1_720p]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference's own shader on the host CPU cores
+
+A "step" is one frame: the per-pixel path (primary DDA + shadow/light rays + shading) over every pixel of
+the frame.  Rays are counted by the REFERENCE's casting rule: W*H primary rays, one global-light
+ray per hit pixel, one local-light ray per (hit pixel, light) the reference shader would cast.
+N > 1: sort-first image-tile split (tile t -> rank t % N), grid replicated, one NCCL all-gather of the RGBA8
+tiles per frame + an un-tile kernel on every rank; total work is fixed => "scaling": "strong".
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {                     # name -> (scene, resolution key)
+    "C3ii_4k": ("C3ii", "4k"),                    # BASELINE configs[2] (ii): 3840x2160, 16 local lights  <- default
+    "C3i_4k": ("C3i", "4k"),                      # configs[2] (i): step-count ("depth field") view
+    "C3ii_pitched_4k": ("C3ii_pitched", "4k"),    # second camera pose
+    "C2_1080p": ("C2", "1080p"),                  # configs[1]
+    "C1_720p": ("C1", "720p"),                    # configs[0] (the reference's CPU-runnable case)
+}
+METRIC = "Mrays/sec (primary+shadow), reference default level, 16 local lights"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C3ii_4k", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads / cpu baseline (profiling runs)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- level / oracle helpers (checker-side only: cpu_baseline and --impl reference) -------------------
+def oracle_handle():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    oracle_lib.build_oracle()
+    return oracle_lib, oracle_lib.Oracle()
+
+
+def default_level():
+    """reference default level with depth field (fingerprint 4c58cc4001a22afa), built by the product's own device
+    builder when a GPU is present (bench arm) -- see make_level_gpu -- or by the oracle (reference arm)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import conftest
+    ol, o = oracle_handle()
+    return conftest.load_default_level(o)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.proc = None
+        self.lines = []
+        self.idx = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power)}
+
+
+# =====================================================================================================
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import voxel_rt_b200 as vx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: libvxrt has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    scene, reskey = WORKLOADS[args.workload]
+    W, H = vx.scenes.RESOLUTIONS[reskey]
+    frame = vx.scenes.frame_for(scene, W, H)
+
+    # ---- grid: every rank builds its replica; level generation + depth field are outside the timed region ----
+    ol, o = oracle_handle()
+    nodepth = o.default_level(depth_field=False)                  # level.cpp:82-138 restated (input generator)
+    ren = vx.Renderer(grid=vx.scenes.DEFAULT_GRID, width=W, height=H, device=local_rank, rank=rank, world=world)
+    ren.updateGeometry(nodepth)
+    ren.buildDepthField()                                         # device depth-field builder (render.cpp:273-286)
+    level_arr = ren.downloadGrid()
+    level_fnv = "%016x" % o.fnv(level_arr)
+    assert level_fnv == "4c58cc4001a22afa", level_fnv            # the reference level, bit for bit
+
+    stream = torch.cuda.ExternalStream(ren.stream_ptr(), device=torch.device("cuda", local_rank))
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    local_bytes = ren.local_bytes()
+    if world > 1:
+        local_t = torch.empty(0)                                  # placeholder; real tensors below
+        gathered = torch.empty(world * local_bytes, dtype=torch.uint8, device="cuda")
+        final = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
+        # zero-copy view of the renderer's device output buffer as a torch tensor
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (local_bytes,), "typestr": "|u1", "data": (ren.device_rgba8_ptr(), False), "version": 3}
+        local_t = torch.as_tensor(_Buf(), device="cuda")
+
+    def step_device():
+        """one frame with inputs resident: kernels (+ gather + un-tile for N > 1) on the renderer's stream"""
+        ren.draw()
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gathered, local_t)
+            ren.assembleTiles(gathered.data_ptr(), final.data_ptr())
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ren.updateUniforms(frame)
+    for _ in range(max(args.warmup, 3)):
+        flush_l2(); step_device()
+    barrier()
+    st = ren.stats()
+    # ---- timed region: K frames, each bracketed by CUDA events on the launching stream, L2 flushed in between ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = {"primary": [], "shade": []}
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush_l2()
+        ev[k][0].record(stream)
+        step_device()
+        ev[k][1].record(stream)
+        if k % 8 == 7 or k == args.steps - 1:
+            ren.sync()
+        # per-kernel CUDA-event durations of this frame (events live inside vxrt_render, same stream)
+        if k % 8 == 7 or k == args.steps - 1:
+            s = ren.stats(); kern_ms["primary"].append(s["ms_primary"]); kern_ms["shade"].append(s["ms_shadow"])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    # MAX over ranks of the summed device time; rays / fetches summed over ranks
+    rays_local_rank = vx.scenes.total_rays(st)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        cnt = torch.tensor([rays_local_rank, st["fetches"], st["hit_pixels"], st["rays_primary"], st["rays_global"], st["rays_local"]],
+                           dtype=torch.int64, device="cuda")
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        rays, fetches, hits, rp, rg, rl = (int(x) for x in cnt.tolist())
+    else:
+        rays, fetches, hits = rays_local_rank, st["fetches"], st["hit_pixels"]
+        rp, rg, rl = st["rays_primary"], st["rays_global"], st["rays_local"]
+    ms_per_step = total_ms / args.steps
+    value = rays / (ms_per_step * 1e-3) / 1e6                    # Mrays/s, whole job
+
+    # ---- e2e: the public C-ABI call with HOST buffers (frame params in, RGBA8 frame out), wall clock ----
+    host_out = np.empty(ren.out_shape(), np.uint8)
+    final_host = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() if world > 1 else None
+
+    def step_e2e():
+        if world == 1:
+            ren.renderFrameHost(frame, host_out)                  # set_frame + kernels + D2H (pinned staging) + sync
+        else:
+            ren.updateUniforms(frame)
+            step_device()
+            with torch.cuda.stream(stream):
+                if rank == 0:
+                    final_host.copy_(final, non_blocking=True)
+            ren.sync()
+    for _ in range(3):
+        flush_l2(); step_e2e()
+    barrier()
+    e2e_s = 0.0
+    for k in range(args.steps):
+        flush_l2(); ren.sync()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        step_e2e()
+        e2e_s += time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = rays / (e2e_s / args.steps) / 1e6
+    h2d = 360                                                     # the frame parameters (kernel arguments)
+    d2h = W * H * 4                                               # the RGBA8 frame (rank 0)
+
+    result = None
+    if rank == 0:
+        hbm, peak_src = peaks()
+        # dominant kernel = the one with the larger share of the frame
+        prim_ms, shade_ms = statistics.mean(kern_ms["primary"]), statistics.mean(kern_ms["shade"])
+        fp = st["fetches_primary"]; fs = st["fetches"] - fp
+        bytes_primary = 4 * fp + 4 * st["rays_primary"] + 360                           # fetches + RGBA8/hit-record store
+        bytes_shade = 4 * fs + 4 * st["hit_pixels"] + 4 * st["hit_pixels"]              # fetches + colour read + RGBA8 store
+        dom = "shade_kernel" if shade_ms >= prim_ms else "primary_kernel"
+        dom_ms, dom_bytes = (shade_ms, bytes_shade) if dom == "shade_kernel" else (prim_ms, bytes_primary)
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s",
+                    "frac": round(achieved / hbm, 5), "traffic": None, "peak_source": peak_src,
+                    "note": "algorithmic bytes = 4 B x castRay iterations + colour read + RGBA8 store per launch (rank 0's tiles); "
+                            "the path is a latency-bound gather, see DESIGN.md",
+                    "kernels": {"primary_kernel": {"ms": round(prim_ms, 4), "alg_bytes": int(bytes_primary)},
+                                "shade_kernel": {"ms": round(shade_ms, 4), "alg_bytes": int(bytes_shade)}}}
+        result = {
+            "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic (reference procedural default level, fnv1a64 %s; fixed camera)" % level_fnv,
+            "config": {"workload": args.workload, "grid": list(vx.scenes.DEFAULT_GRID), "width": W, "height": H, "local_lights": 16 if scene != "C1" else 0,
+                       "view_depth_field": int(frame.view_depth_field), "rays_per_frame": rays, "rays_primary": rp, "rays_global": rg,
+                       "rays_local": rl, "voxel_fetches_per_frame": fetches, "hit_pixels": hits,
+                       "partition": "sort-first 32x8 tiles, tile t -> rank t %% %d, grid replicated, NCCL all-gather of RGBA8 tiles" % world,
+                       "l2": "flushed between timed frames (256 MiB write)", "timing": "CUDA events on the launching stream per frame, max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "vxrt_render_frame_host (C ABI): host frame params in, host RGBA8 frame out; wall clock"},
+            "gpu_launches": int(args.steps * (st["kernel_launches"] + (1 if world > 1 else 0))),
+            "roofline": roofline,
+            "wall_s_timed_region": round(t_wall, 3),
+        }
+        if not args.no_extra and world == 1:
+            result["other_workloads"] = extra_workloads(vx, ren, flush_l2, stream, torch)
+            result["cpu_baseline"] = cpu_baseline(args.workload, level=level_arr)
+    ren.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(result))
+
+
+def extra_workloads(vx, ren, flush_l2, stream, torch, steps=10):
+    """secondary single-GPU measurements (same timing discipline), reported beside the headline workload"""
+    out = {}
+    for name in ("C2_1080p", "C3i_4k", "C3ii_pitched_4k", "C1_720p"):
+        scene, reskey = WORKLOADS[name]
+        W, H = vx.scenes.RESOLUTIONS[reskey]
+        ren.reshape(W, H)
+        ren.updateUniforms(vx.scenes.frame_for(scene, W, H))
+        for _ in range(3):
+            flush_l2(); ren.draw()
+        ren.sync()
+        ms = []
+        for _ in range(steps):
+            flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); ren.draw(); b.record(stream); ren.sync()
+            ms.append(a.elapsed_time(b))
+        st = ren.stats()
+        rays = vx.scenes.total_rays(st)
+        m = statistics.mean(ms)
+        out[name] = {"ms_per_frame": round(m, 4), "Mrays_per_s": round(rays / (m * 1e-3) / 1e6, 2), "rays_per_frame": rays,
+                     "voxel_fetches_per_frame": st["fetches"]}
+    return out
+
+
+# =====================================================================================================
+def reference_frame_runner(workload, stride, level=None):
+    """Returns (run_once() -> seconds, rays_in_sample, kind, cores, sample_description).  Uses the reference's own
+    shader compiled for the CPU (oracle/_ref/ref_shader_cli, all host cores via fork) when that build travelled
+    with the repo, else the oracle port (OpenMP, all cores)."""
+    import voxel_rt_b200 as vx
+    ol, o = oracle_handle()
+    scene, reskey = WORKLOADS[workload]
+    W, H = vx.scenes.RESOLUTIONS[reskey]
+    fr_vx = vx.scenes.frame_for(scene, W, H)
+    fr = ol.Frame()
+    C.memmove(C.byref(fr), C.byref(fr_vx), C.sizeof(fr))
+    if level is None:
+        level = default_level()
+    cores = os.cpu_count() or 1
+    rows = [y for y in range(H) if ((y >> 3) % stride) == 0]
+    # rays of the sample, counted by the oracle (untimed)
+    counters = np.zeros(5, np.uint64)
+    blocks = sorted(set(y >> 3 for y in rows))
+    for b in blocks:
+        out = o.render(level, (512, 96, 512), fr, W, H, y0=b * 8, y1=min(H, b * 8 + 8))
+        counters += out["counters"]
+    rays = int(counters[0] + counters[1] + counters[2])
+    sample = "%s: %d of %d rows (8-row blocks, every %d%s block), %d rays" % (workload, len(rows), H, stride, "th" if stride > 1 else "", rays)
+    cli = os.path.join(ROOT, "oracle", "_ref", "ref_shader_cli")
+    if os.path.exists(cli) and os.access(cli, os.X_OK):
+        tmp = tempfile.mkdtemp(prefix="vxrt_ref_")
+        gpath, fpath = os.path.join(tmp, "grid.i32"), os.path.join(tmp, "frame.bin")
+        level.tofile(gpath)
+        buf = np.zeros(90, np.float32)
+        buf[:89] = fr.to89()
+        buf[89:90].view(np.int32)[0] = fr.view_depth_field
+        buf.tofile(fpath)
+
+        def run(reps):
+            r = subprocess.run([cli, gpath, fpath, str(W), str(H), str(cores), str(reps), str(stride)], capture_output=True, text=True, check=True)
+            return [float(x) for x in r.stdout.split()]
+        return run, rays, "reference", cores, sample + "; unmodified fshader.glsl compiled for the CPU via the reference's GLM, %d forked workers" % cores
+
+    def run(reps):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            for b in blocks:
+                o.render(level, (512, 96, 512), fr, W, H, y0=b * 8, y1=min(H, b * 8 + 8))
+            ts.append(time.perf_counter() - t0)
+        return ts
+    return run, rays, "port", o.num_threads(), sample + "; C restatement (oracle/vxo.c), OpenMP"
+
+
+def cpu_baseline(workload, level=None):
+    """bounded CPU sample of the same workload on this box's host cores (reported, not targeted)"""
+    try:
+        run, rays, kind, cores, sample = reference_frame_runner(workload, stride=4, level=level)
+        ts = run(2)
+        t = min(ts)
+        return {"value": round(rays / t / 1e6, 3), "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample,
+                "seconds_per_sample": round(t, 4)}
+    except Exception as e:                                         # the baseline must never take the bench line down
+        return {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import voxel_rt_b200 as vx
+    scene, reskey = WORKLOADS[args.workload]
+    W, H = vx.scenes.RESOLUTIONS[reskey]
+    # size the per-step sample so that (warmup + steps) samples end within ~2 minutes
+    level = default_level()
+    run, rays_full, kind, cores, _ = reference_frame_runner(args.workload, stride=16, level=level)
+    t_probe = min(run(1)) * 16.0                                  # ~ full-frame seconds
+    budget = 120.0
+    n = args.steps + args.warmup
+    stride = 1
+    while stride < 64 and t_probe / stride * n > budget:
+        stride *= 2
+    run, rays, kind, cores, sample = reference_frame_runner(args.workload, stride=stride, level=level)
+    if args.warmup:
+        run(args.warmup)
+    ts = run(args.steps)
+    ms = statistics.mean(ts) * 1e3
+    value = rays / (ms * 1e-3) / 1e6
+    frame = vx.scenes.frame_for(scene, W, H)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (reference procedural default level, fnv1a64 4c58cc4001a22afa; fixed camera)",
+        "config": {"workload": args.workload, "grid": [512, 96, 512], "width": W, "height": H, "local_lights": 16 if scene != "C1" else 0,
+                   "view_depth_field": int(frame.view_depth_field), "rays_per_step_sample": rays},
+        "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,151 @@
+/*
+ * vxrt.h -- C ABI of libvxrt.so, the B200 (sm_100a) implementation of voxel-rt's per-pixel hot path.
+ *
+ * The reference (Berry2460/voxel-rt) has no plugin API; its seam is src/render.hpp:30-41 plus the
+ * OpenGL calls src/render.cpp makes (glBufferData / glBufferSubData / glUniform* / glDrawArrays).
+ * Every entry point below names the reference interface it replaces (file:line under src/).
+ * Plain pointers and sizes only; no C++/torch types.  All functions return 0 on success and a
+ * negative vxrt_status on failure (the reference surfaces no errors at all; its render.hpp shim
+ * may ignore them); vxrt_last_error() gives the message of the calling thread's last failure.
+ *
+ * Threading: like the reference's GL usage, one caller thread per context.
+ * Ownership: upload calls COPY from the caller's (pageable or pinned) memory at call time, exactly
+ * like glBufferData / glBufferSubData; the host array stays the caller's.
+ *
+ * Frame buffers use the GL window convention: row 0 is the BOTTOM row.
+ */
+#ifndef VXRT_H
+#define VXRT_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VXRT_MAX_LOCAL_LIGHTS 16     /* render.hpp:11, fshader.glsl:6 */
+#define VXRT_TILE_W 32               /* image-tile partition unit (multi-GPU sort-first split) */
+#define VXRT_TILE_H 8
+
+typedef enum {
+    VXRT_OK = 0,
+    VXRT_ERR_INVALID = -1,           /* bad argument */
+    VXRT_ERR_CUDA = -2,              /* CUDA runtime failure (message has the cudaError string) */
+    VXRT_ERR_NO_DEVICE = -3,         /* no usable sm_100 device: there is NO CPU fallback */
+    VXRT_ERR_STATE = -4,             /* call out of order (e.g. render before any grid upload) */
+    VXRT_ERR_IO = -5
+} vxrt_status;
+
+typedef struct vxrt_ctx vxrt_ctx;
+
+/* flags */
+#define VXRT_FLAG_DEBUG_OUTPUTS 1u   /* keep per-pixel hit index / step count / shadow masks (parity tests) */
+
+typedef struct {
+    int32_t grid_w, grid_h, grid_d;  /* voxel grid extents; reference: 512, 96, 512 (render.hpp:4-5) */
+    int32_t width, height;           /* frame size in pixels (main.cpp:11-12, reshape render.cpp:404-411) */
+    int32_t device;                  /* CUDA device ordinal */
+    int32_t rank, world;             /* image-tile partition: this context renders tiles t with t % world == rank */
+    uint32_t flags;
+} vxrt_config;
+
+/* == the shader's uniforms, fshader.glsl:20-26, as written by updateUniforms() render.cpp:289-296 */
+typedef struct {
+    float cam_pos[3];
+    float cam_rotation[2];           /* uploaded by the reference, never read by its shader */
+    float light_pos[3];
+    float aspect;
+    float rotate[16];                /* column-major mat4 (render.cpp:294, GL_FALSE) */
+    int32_t view_depth_field;        /* 1 = step-count view (fshader.glsl:143-145) */
+    float lights[VXRT_MAX_LOCAL_LIGHTS][4];   /* xyz + diffuse weight; slot inactive if any of xyz < 0 */
+} vxrt_frame;
+
+typedef struct {
+    /* ray counts by the REFERENCE's casting rule: primary = pixels rendered by this context;
+       global = one per hit pixel; local = one per (hit pixel, light) the reference shader would cast */
+    uint64_t rays_primary, rays_global, rays_local;
+    uint64_t fetches;                /* castRay iterations == voxel fetches of the reference algorithm */
+    uint64_t fetches_primary;        /* ... of which by primary rays (the rest: shadow / light rays) */
+    uint64_t hit_pixels;
+    float ms_primary, ms_shadow, ms_total;   /* CUDA-event times of the last vxrt_render */
+    uint32_t kernel_launches;        /* kernels launched by the last vxrt_render */
+} vxrt_stats;
+
+/* ---- lifetime --------------------------------------------------------------------------------- */
+/* replaces initRender()'s GL object / SSBO creation, render.cpp:313-372 */
+int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out);
+void vxrt_destroy(vxrt_ctx* ctx);
+const char* vxrt_last_error(void);
+/* 1 iff a device of compute capability 10.x is present */
+int vxrt_device_available(void);
+
+/* ---- grid ------------------------------------------------------------------------------------- */
+/* updateGeometry() render.cpp:199-202 / glBufferData render.cpp:368: whole grid, count must equal w*h*d */
+int vxrt_upload_grid(vxrt_ctx* ctx, const int32_t* voxels, size_t count);
+/* one glBufferSubData(offset=first*4, size=count*4, &voxels[first]) render.cpp:219 */
+int vxrt_upload_range(vxrt_ctx* ctx, size_t first, size_t count, const int32_t* src);
+/* updatePartialGeometry(start,end) render.cpp:204-223, with its row-skipping / wrapping behaviour, as ONE
+   staged copy + scatter kernel; host_voxels is the caller's full grid (the reference's voxels[]).
+   Rows that would run past the end of the buffer are dropped (GL_INVALID_VALUE in the reference).
+   *rows_out (optional) receives the number of rows uploaded (the reference's glBufferSubData call count). */
+int vxrt_update_partial(vxrt_ctx* ctx, const float start[3], const float end[3], const int32_t* host_voxels,
+                        int32_t* rows_out);
+int vxrt_download_grid(vxrt_ctx* ctx, int32_t* out, size_t count);
+/* copy the device box [lo,hi) (clamped to the grid) into the caller's FULL-GRID array (host mirror sync after
+   a device-side edit; the reference's CPU collision code reads voxels[], controls.cpp:10-19) */
+int vxrt_download_box(vxrt_ctx* ctx, const int32_t lo[3], const int32_t hi[3], int32_t* host_voxels);
+
+/* placeVoxel render.cpp:256-262 / destroyVoxel render.cpp:265-271 applied to the device grid */
+int vxrt_place_voxel(vxrt_ctx* ctx, int x, int y, int z, int32_t voxel);
+int vxrt_destroy_voxel(vxrt_ctx* ctx, int x, int y, int z);
+/* removeSphere(pos, radius) level.cpp:30-56 executed on the device grid (carve + fixDepthField over the
+   radius+3 sphere); no host upload needed afterwards */
+int vxrt_edit_remove_sphere(vxrt_ctx* ctx, int cx, int cy, int cz, int radius);
+/* computeDepthField sweep over the whole grid, render.cpp:226-253,273-286 (out-of-grid neighbours = solid) */
+int vxrt_build_depth_field(vxrt_ctx* ctx);
+
+/* ---- frame ------------------------------------------------------------------------------------ */
+/* updateUniforms() render.cpp:289-296 */
+int vxrt_set_frame(vxrt_ctx* ctx, const vxrt_frame* frame);
+/* initLocalLights() render.cpp:304-311 / placeLocalLight() render.cpp:375-385 acting on the context's frame;
+   place returns the slot used (>= 0) or VXRT_MAX_LOCAL_LIGHTS when all slots are taken (silently ignored) */
+int vxrt_init_local_lights(vxrt_ctx* ctx);
+int vxrt_place_local_light(vxrt_ctx* ctx, float x, float y, float z, float diffuse);
+int vxrt_get_frame(vxrt_ctx* ctx, vxrt_frame* out);
+/* reshape() render.cpp:404-411: new frame size; aspect := (float)width/height */
+int vxrt_resize(vxrt_ctx* ctx, int width, int height);
+/* glDrawArrays(GL_TRIANGLES,0,6) main.cpp:59: runs the per-pixel path for this context's tiles; asynchronous */
+int vxrt_render(vxrt_ctx* ctx);
+int vxrt_sync(vxrt_ctx* ctx);
+/* set_frame + render + device->host copy of the RGBA8 frame into out (width*height*4 bytes) + sync.
+   world > 1: out receives this rank's tiles in gather layout (vxrt_local_bytes()). */
+int vxrt_render_frame_host(vxrt_ctx* ctx, const vxrt_frame* frame, uint8_t* out);
+
+/* ---- results ---------------------------------------------------------------------------------- */
+int vxrt_read_rgba8(vxrt_ctx* ctx, uint8_t* out);            /* width*height*4 (world==1) else vxrt_local_bytes() */
+/* parity outputs (need VXRT_FLAG_DEBUG_OUTPUTS); full-frame arrays, any pointer may be NULL:
+   hit_index: primary castRay result (-1 miss); steps: primary stepCount; occl_mask bit0 = global-light ray
+   occluded, bit(1+i) = local light i occluded; cast_mask: same bits, "ray was cast" */
+int vxrt_read_debug(vxrt_ctx* ctx, int32_t* hit_index, uint16_t* steps, uint32_t* occl_mask, uint32_t* cast_mask);
+int vxrt_get_stats(vxrt_ctx* ctx, vxrt_stats* out);
+/* known-answer hook: castRay(start, dir, dist) fshader.glsl:59-129 for n independent rays (host arrays:
+   starts/dirs n*3 floats, dists n ints); ret[n] = return value, out7[n*7] = hitPos[3] hitNormal[3] stepCount */
+int vxrt_cast_rays(vxrt_ctx* ctx, int32_t n, const float* starts, const float* dirs, const int32_t* dists,
+                   int32_t* ret, float* out7);
+/* binary PPM (P6), rows flipped so the image is upright */
+int vxrt_write_ppm(vxrt_ctx* ctx, const char* path);
+
+/* ---- multi-GPU plumbing (device pointers; the collective itself is the caller's, e.g. NCCL all-gather) -- */
+size_t vxrt_local_tiles(vxrt_ctx* ctx);                      /* tiles per rank (padded: ceil(tiles/world)) */
+size_t vxrt_local_bytes(vxrt_ctx* ctx);                      /* local_tiles * TILE_W*TILE_H*4 */
+void*  vxrt_device_rgba8(vxrt_ctx* ctx);                     /* device pointer of this rank's output buffer */
+void*  vxrt_stream(vxrt_ctx* ctx);                           /* cudaStream_t the context launches on */
+/* gathered: device pointer to world * vxrt_local_bytes() bytes (rank-major, as produced by an all-gather of
+   vxrt_device_rgba8()); dst: device pointer to width*height*4 bytes; un-tiles into a raster frame on
+   `stream` (NULL = the context's stream) */
+int vxrt_assemble_tiles(vxrt_ctx* ctx, const void* gathered, void* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -98,12 +98,17 @@ void ref_shader_pixel(int px, int py, int width, int height, float rgba[4], floa
     if (total_steps) *total_steps = stepCount;
 }
 
+static int g_row_stride = 1;     // bounded samples: only 8-row blocks b with b % stride == 0 are rendered
+void ref_shader_set_row_stride(int s) { g_row_stride = s < 1 ? 1 : s; }
+
 static void render_rows(int width, int height, int y0, int y1, float* rgba, float* total_steps) {
-    for (int py = y0; py < y1; py++)
+    for (int py = y0; py < y1; py++) {
+        if (((py >> 3) % g_row_stride) != 0) continue;
         for (int px = 0; px < width; px++) {
             size_t p = (size_t)py * width + px;
             ref_shader_pixel(px, py, width, height, rgba + 4 * p, total_steps ? total_steps + p : nullptr);
         }
+    }
 }
 
 // Rows [y0,y1) into full-frame arrays.  The shader's globals make it single-threaded per process, so
@@ -142,13 +147,13 @@ int ref_shader_render(int width, int height, int y0, int y1, float* rgba, float*
 #ifdef VXRT_REF_SHADER_MAIN
 // Stand-alone timing / dump tool (used by bench.py --impl reference so that the fork()s do not happen
 // inside a Python process):
-//   ref_shader_cli <grid.i32> <frame89+view.bin> <width> <height> <nproc> <reps> [out_rgba.f32]
-// prints one line: "seconds_per_frame_min seconds_per_frame_median"
+//   ref_shader_cli <grid.i32> <frame89+view.bin> <width> <height> <nproc> <reps> <row_stride> [out_rgba.f32]
+// prints one line per repetition: "seconds"
 #include <chrono>
 #include <vector>
 #include <algorithm>
 int main(int argc, char** argv) {
-    if (argc < 7) { fprintf(stderr, "usage: %s grid.i32 frame.bin width height nproc reps [out.f32]\n", argv[0]); return 2; }
+    if (argc < 8) { fprintf(stderr, "usage: %s grid.i32 frame.bin width height nproc reps row_stride [out.f32]\n", argv[0]); return 2; }
     FILE* fg = fopen(argv[1], "rb"); if (!fg) { perror("grid"); return 1; }
     if (fread(voxels, 1, sizeof(voxels), fg) != sizeof(voxels)) { fprintf(stderr, "short grid file\n"); return 1; }
     fclose(fg);
@@ -158,6 +163,7 @@ int main(int argc, char** argv) {
     int view; memcpy(&view, &fr[89], 4);
     ref_shader_set_uniforms(fr, view);
     int width = atoi(argv[3]), height = atoi(argv[4]), nproc = atoi(argv[5]), reps = atoi(argv[6]);
+    ref_shader_set_row_stride(atoi(argv[7]));
     std::vector<float> rgba((size_t)width * height * 4);
     std::vector<double> t;
     for (int r = 0; r < reps; r++) {
@@ -165,10 +171,10 @@ int main(int argc, char** argv) {
         if (ref_shader_render(width, height, 0, height, rgba.data(), nullptr, nproc) != 0) return 1;
         auto b = std::chrono::steady_clock::now();
         t.push_back(std::chrono::duration<double>(b - a).count());
+        fflush(stdout);
     }
-    std::sort(t.begin(), t.end());
-    printf("%.6f %.6f\n", t.front(), t[t.size() / 2]);
-    if (argc > 7) { FILE* fo = fopen(argv[7], "wb"); fwrite(rgba.data(), 4, rgba.size(), fo); fclose(fo); }
+    for (double x : t) printf("%.6f\n", x);
+    if (argc > 8) { FILE* fo = fopen(argv[8], "wb"); fwrite(rgba.data(), 4, rgba.size(), fo); fclose(fo); }
     return 0;
 }
 #endif

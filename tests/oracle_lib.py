@@ -204,6 +204,14 @@ class RefHost:
                                             frame.rotate, C.c_int(frame.view_depth_field), _ptr(out, C.c_float))
         return out, v
 
+    def place_light(self, x, y, z, w):
+        self.L.ref_host_place_light(C.c_float(x), C.c_float(y), C.c_float(z), C.c_float(w))
+
+    def lights(self):
+        out = np.zeros(64, np.float32)
+        self.L.ref_host_get_lights(_ptr(out, C.c_float))
+        return out.reshape(16, 4)
+
     def mouse_look(self, rx, ry):
         rot = np.zeros(16, np.float32)
         d = np.zeros(3, np.float32)

@@ -1,0 +1,309 @@
+"""Host-side mirror of the reference's render interface (src/render.hpp:30-41) over the C ABI of libvxrt.so.
+
+`Renderer` keeps the reference's function names (updateGeometry, updatePartialGeometry, placeVoxel,
+destroyVoxel, removeSphere, updateUniforms, reshape, placeLocalLight, ...) so callers and tests read like
+the reference's own host code; every method is a thin ctypes call into include/vxrt.h.  There is no CPU
+fallback: constructing a Renderer without an sm_100 GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+MAX_LOCAL_LIGHTS = 16
+TILE_W, TILE_H = 32, 8
+FLAG_DEBUG_OUTPUTS = 1
+
+
+class VxrtError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("grid_w", C.c_int32), ("grid_h", C.c_int32), ("grid_d", C.c_int32),
+                ("width", C.c_int32), ("height", C.c_int32), ("device", C.c_int32),
+                ("rank", C.c_int32), ("world", C.c_int32), ("flags", C.c_uint32)]
+
+
+class Frame(C.Structure):
+    """== vxrt_frame: the shader's uniforms (fshader.glsl:20-26, render.cpp:289-296)."""
+    _fields_ = [("cam_pos", C.c_float * 3), ("cam_rotation", C.c_float * 2), ("light_pos", C.c_float * 3),
+                ("aspect", C.c_float), ("rotate", C.c_float * 16), ("view_depth_field", C.c_int32),
+                ("lights", (C.c_float * 4) * MAX_LOCAL_LIGHTS)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("rays_primary", C.c_uint64), ("rays_global", C.c_uint64), ("rays_local", C.c_uint64),
+                ("fetches", C.c_uint64), ("fetches_primary", C.c_uint64), ("hit_pixels", C.c_uint64),
+                ("ms_primary", C.c_float), ("ms_shadow", C.c_float), ("ms_total", C.c_float),
+                ("kernel_launches", C.c_uint32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# every symbol include/vxrt.h declares (checked by tests/test_cabi.py against the header text)
+_SIGNATURES = {
+    "vxrt_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "vxrt_destroy": (None, [C.c_void_p]),
+    "vxrt_last_error": (C.c_char_p, []),
+    "vxrt_device_available": (C.c_int, []),
+    "vxrt_upload_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "vxrt_upload_range": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "vxrt_update_partial": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.POINTER(C.c_int32)]),
+    "vxrt_download_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "vxrt_download_box": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]),
+    "vxrt_place_voxel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int32]),
+    "vxrt_destroy_voxel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "vxrt_edit_remove_sphere": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vxrt_build_depth_field": (C.c_int, [C.c_void_p]),
+    "vxrt_set_frame": (C.c_int, [C.c_void_p, C.POINTER(Frame)]),
+    "vxrt_init_local_lights": (C.c_int, [C.c_void_p]),
+    "vxrt_place_local_light": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]),
+    "vxrt_get_frame": (C.c_int, [C.c_void_p, C.POINTER(Frame)]),
+    "vxrt_resize": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "vxrt_render": (C.c_int, [C.c_void_p]),
+    "vxrt_sync": (C.c_int, [C.c_void_p]),
+    "vxrt_render_frame_host": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p]),
+    "vxrt_read_rgba8": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vxrt_read_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vxrt_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "vxrt_cast_rays": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vxrt_write_ppm": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "vxrt_local_tiles": (C.c_size_t, [C.c_void_p]),
+    "vxrt_local_bytes": (C.c_size_t, [C.c_void_p]),
+    "vxrt_device_rgba8": (C.c_void_p, [C.c_void_p]),
+    "vxrt_stream": (C.c_void_p, [C.c_void_p]),
+    "vxrt_assemble_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load_library(build_if_missing=True):
+    """dlopen libvxrt.so (building it first if the sources are newer).  Fails loudly if it cannot be loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.lib_path()
+    if build_if_missing and _build.needs_build():
+        _build.build()
+    if not os.path.exists(path):
+        raise VxrtError("libvxrt.so is missing (%s): build it with `python -m voxel_rt_b200.build`; there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def make_frame(cam_pos, rotate=None, light_pos=(256.0, 1536.0, 256.0), aspect=16.0 / 9.0, view=0, lights=None,
+               cam_rotation=(0.0, 0.0)):
+    """Frame parameters as updateUniforms() would send them (render.cpp:289-296); unused light slots are
+    (-1,-1,-1,0) like initLocalLights() (render.cpp:304-311)."""
+    f = Frame()
+    f.cam_pos[:] = [float(np.float32(v)) for v in cam_pos]
+    f.cam_rotation[:] = [float(v) for v in cam_rotation]
+    f.light_pos[:] = [float(np.float32(v)) for v in light_pos]
+    f.aspect = float(np.float32(aspect))
+    rot = np.eye(4, dtype=np.float32).ravel() if rotate is None else np.asarray(rotate, np.float32).ravel()
+    f.rotate[:] = [float(v) for v in rot]
+    f.view_depth_field = int(view)
+    for i in range(MAX_LOCAL_LIGHTS):
+        f.lights[i][:] = [-1.0, -1.0, -1.0, 0.0]
+    if lights is not None:
+        for i, l in enumerate(lights):
+            f.lights[i][:] = [float(np.float32(v)) for v in l]
+    return f
+
+
+def _vp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Renderer:
+    """One context = one GPU's replica of the voxel grid plus the frame state (the reference's globals in
+    main.cpp:26-37 and GL objects in render.cpp)."""
+
+    def __init__(self, grid=(512, 96, 512), width=800, height=600, device=0, rank=0, world=1, debug=False):
+        self.lib = load_library()
+        self.grid = tuple(int(v) for v in grid)
+        self.width, self.height = int(width), int(height)
+        self.rank, self.world = int(rank), int(world)
+        self.debug = bool(debug)
+        cfg = Config(self.grid[0], self.grid[1], self.grid[2], self.width, self.height, int(device), self.rank, self.world,
+                     FLAG_DEBUG_OUTPUTS if debug else 0)
+        h = C.c_void_p()
+        self._h = None
+        self._check(self.lib.vxrt_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    # -- plumbing --
+    def _check(self, rc):
+        if rc < 0:
+            raise VxrtError("libvxrt error %d: %s" % (rc, self.lib.vxrt_last_error().decode()))
+        return rc
+
+    def close(self):
+        if self._h is not None:
+            self.lib.vxrt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def nvox(self):
+        return self.grid[0] * self.grid[1] * self.grid[2]
+
+    # -- render.hpp:30-41 mirror --
+    def updateGeometry(self, voxels):
+        """render.cpp:199-202: whole-grid upload."""
+        v = np.ascontiguousarray(voxels, np.int32).ravel()
+        self._check(self.lib.vxrt_upload_grid(self._h, _vp(v), v.size))
+
+    def uploadRange(self, first, src):
+        """one glBufferSubData (render.cpp:219)."""
+        s = np.ascontiguousarray(src, np.int32).ravel()
+        self._check(self.lib.vxrt_upload_range(self._h, int(first), s.size, _vp(s)))
+
+    def updatePartialGeometry(self, start, end, host_voxels):
+        """render.cpp:204-223; returns the number of rows uploaded."""
+        v = host_voxels
+        assert v.dtype == np.int32 and v.flags.c_contiguous and v.size == self.nvox
+        rows = C.c_int32(0)
+        s = (C.c_float * 3)(*[float(x) for x in start])
+        e = (C.c_float * 3)(*[float(x) for x in end])
+        self._check(self.lib.vxrt_update_partial(self._h, s, e, _vp(v), C.byref(rows)))
+        return rows.value
+
+    def placeVoxel(self, x, y, z, voxel):
+        self._check(self.lib.vxrt_place_voxel(self._h, x, y, z, voxel))
+
+    def destroyVoxel(self, x, y, z):
+        self._check(self.lib.vxrt_destroy_voxel(self._h, x, y, z))
+
+    def removeSphere(self, pos, radius):
+        """level.cpp:30-56 on the device grid."""
+        self._check(self.lib.vxrt_edit_remove_sphere(self._h, int(pos[0]), int(pos[1]), int(pos[2]), int(radius)))
+
+    def doDestroy(self, cam_pos, cam_dir, host_voxels=None):
+        """controls.cpp:100-110: centre = camPos + 15*camDir, removeSphere(ivec3(centre), 7); instead of
+        updatePartialGeometry the edit already happened on the device; the host mirror (if given) is synced
+        from the touched box."""
+        c = [np.float32(cam_pos[k]) + np.float32(15.0) * np.float32(cam_dir[k]) for k in range(3)]
+        ic = [int(np.trunc(v)) for v in c]
+        self.removeSphere(ic, 7)
+        if host_voxels is not None:
+            self.downloadBox([v - 10 for v in ic], [v + 10 for v in ic], host_voxels)
+        return ic
+
+    def buildDepthField(self):
+        """computeDepthField sweep (render.cpp:273-286) on the device."""
+        self._check(self.lib.vxrt_build_depth_field(self._h))
+
+    def downloadGrid(self):
+        out = np.empty(self.nvox, np.int32)
+        self._check(self.lib.vxrt_download_grid(self._h, _vp(out), out.size))
+        return out
+
+    def downloadBox(self, lo, hi, host_voxels):
+        assert host_voxels.dtype == np.int32 and host_voxels.flags.c_contiguous and host_voxels.size == self.nvox
+        l = (C.c_int32 * 3)(*[int(v) for v in lo])
+        h = (C.c_int32 * 3)(*[int(v) for v in hi])
+        self._check(self.lib.vxrt_download_box(self._h, l, h, _vp(host_voxels)))
+
+    def updateUniforms(self, frame):
+        self._check(self.lib.vxrt_set_frame(self._h, C.byref(frame)))
+
+    def initLocalLights(self):
+        self._check(self.lib.vxrt_init_local_lights(self._h))
+
+    def placeLocalLight(self, x, y, z, diffuse):
+        return self._check(self.lib.vxrt_place_local_light(self._h, x, y, z, diffuse))
+
+    def getFrame(self):
+        f = Frame()
+        self._check(self.lib.vxrt_get_frame(self._h, C.byref(f)))
+        return f
+
+    def reshape(self, width, height):
+        self._check(self.lib.vxrt_resize(self._h, int(width), int(height)))
+        self.width, self.height = int(width), int(height)
+
+    def draw(self):
+        """glDrawArrays(GL_TRIANGLES,0,6) main.cpp:59 (asynchronous)."""
+        self._check(self.lib.vxrt_render(self._h))
+
+    def sync(self):
+        self._check(self.lib.vxrt_sync(self._h))
+
+    # -- results --
+    def local_bytes(self):
+        return int(self.lib.vxrt_local_bytes(self._h))
+
+    def out_shape(self):
+        return (self.height, self.width, 4) if self.world == 1 else (self.local_bytes() // (TILE_W * TILE_H * 4), TILE_H, TILE_W, 4)
+
+    def renderFrameHost(self, frame, out=None):
+        """updateUniforms + draw + read-back to host memory in one call (the end-to-end path)."""
+        if out is None:
+            out = np.empty(self.out_shape(), np.uint8)
+        self._check(self.lib.vxrt_render_frame_host(self._h, C.byref(frame), _vp(out)))
+        return out
+
+    def readPixels(self):
+        out = np.empty(self.out_shape(), np.uint8)
+        self._check(self.lib.vxrt_read_rgba8(self._h, _vp(out)))
+        return out
+
+    def readDebug(self):
+        n = (self.height, self.width)
+        hit = np.empty(n, np.int32)
+        steps = np.empty(n, np.uint16)
+        occl = np.empty(n, np.uint32)
+        cast = np.empty(n, np.uint32)
+        self._check(self.lib.vxrt_read_debug(self._h, _vp(hit), _vp(steps), _vp(occl), _vp(cast)))
+        return dict(hit_index=hit, steps=steps, occl_mask=occl, cast_mask=cast)
+
+    def stats(self):
+        s = Stats()
+        self._check(self.lib.vxrt_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def castRays(self, starts, dirs, dists):
+        """castRay known-answer hook (fshader.glsl:59-129): returns (ret[n], out7[n,7])."""
+        starts = np.ascontiguousarray(starts, np.float32)
+        dirs = np.ascontiguousarray(dirs, np.float32)
+        dists = np.ascontiguousarray(dists, np.int32)
+        n = len(dists)
+        ret = np.zeros(n, np.int32)
+        out7 = np.zeros((n, 7), np.float32)
+        self._check(self.lib.vxrt_cast_rays(self._h, n, _vp(starts), _vp(dirs), _vp(dists), _vp(ret), _vp(out7)))
+        return ret, out7
+
+    def writePPM(self, path):
+        self._check(self.lib.vxrt_write_ppm(self._h, str(path).encode()))
+
+    # -- multi-GPU plumbing --
+    def device_rgba8_ptr(self):
+        return int(self.lib.vxrt_device_rgba8(self._h))
+
+    def stream_ptr(self):
+        return int(self.lib.vxrt_stream(self._h) or 0)
+
+    def assembleTiles(self, gathered_ptr, dst_ptr, stream_ptr=0):
+        self._check(self.lib.vxrt_assemble_tiles(self._h, C.c_void_p(gathered_ptr), C.c_void_p(dst_ptr), C.c_void_p(stream_ptr)))

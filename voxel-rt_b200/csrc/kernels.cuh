@@ -1,0 +1,289 @@
+// kernels.cuh -- the sm_100a kernels of the per-pixel path and of the grid plumbing around it.
+//
+//   primary_kernel   fshader.glsl:131-145 + :59-129   one thread per pixel, 8x4-pixel warps inside 32x8 tiles;
+//                    misses / step-count view are finished here, hits are ballot-compacted into a hit queue
+//   shade_kernel     fshader.glsl:147-187             one thread per queued hit pixel: global shadow ray, the
+//                    sequential local-light loop (light list compacted into shared memory), shading, store
+//   depth_kernel     render.cpp:226-253               fixDepthField for every cell of a box / lopsided sphere
+//   carve_kernel     level.cpp:31-42                  removeSphere's destroy pass
+//   scatter_rows     render.cpp:204-223               updatePartialGeometry's rows, one staged copy + scatter
+//   assemble_kernel  multi-GPU: un-tile the all-gathered per-rank tile buffers into a raster frame
+#pragma once
+#include "ray.cuh"
+
+namespace vxrt {
+
+struct FrameParams {                    // == vxrt_frame (include/vxrt.h), fshader.glsl:20-26
+    float cam_pos[3];
+    float cam_rotation[2];
+    float light_pos[3];
+    float aspect;
+    float rotate[16];
+    int32_t view_depth_field;
+    float lights[16][4];
+};
+
+constexpr int TILE_W = 32, TILE_H = 8, TILE_PIX = TILE_W * TILE_H;
+
+struct TileMap {
+    int width, height;
+    int tx, ty, ntiles;                 // tiles per row / column / total
+    int rank, world, nlocal;            // this context renders tiles t = j*world + rank, j in [0,nlocal)
+};
+
+struct Counters {
+    unsigned int hit_count;
+    unsigned int pad;
+    unsigned long long rays_local, fetches_primary, fetches_shadow;
+};
+
+struct Outputs {
+    uint32_t* rgba8;                    // world==1: raster [height][width]; else tile-compact [nlocal][8][32]
+    float4* hitq;                       // hit queue: hitPos.xyz, w = colour(24) | normal(4)<<24
+    uint32_t* hitpix;                   // raster pixel id of each queue entry
+    Counters* counters;
+    int32_t* dbg_hit;                   // optional (VXRT_FLAG_DEBUG_OUTPUTS), raster layout
+    uint16_t* dbg_steps;
+    uint32_t* dbg_occl;
+    uint32_t* dbg_cast;
+};
+
+__device__ __forceinline__ uint32_t out_index_of(const TileMap& m, int px, int py) {
+    if (m.world == 1) return (uint32_t)(py * m.width + px);
+    const int t = (py / TILE_H) * m.tx + (px / TILE_W);
+    const int local = t / m.world;
+    return (uint32_t)(local * TILE_PIX + (py % TILE_H) * TILE_W + (px % TILE_W));
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) primary_kernel(GridView g, const __grid_constant__ FrameParams f,
+                                                      TileMap m, Outputs o) {
+    __shared__ unsigned int s_warp_hits[8];
+    __shared__ unsigned int s_base;
+    __shared__ unsigned long long s_fetches;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) s_fetches = 0ull;
+    const int t = blockIdx.x * m.world + m.rank;                    // global tile
+    const int lx = (warp & 3) * 8 + (lane & 7), ly = (warp >> 2) * 4 + (lane >> 3);
+    const int px = (t % m.tx) * TILE_W + lx, py = (t / m.tx) * TILE_H + ly;
+    const bool valid = (t < m.ntiles) && (px < m.width) && (py < m.height);
+
+    bool hit = false;
+    RayHit r; r.steps = 0; r.idx = -1;
+    if (valid) {
+        // vshader.glsl:6-9 + quad render.cpp:36-44: vPos = NDC of the pixel centre
+        const float vx = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn((float)px, 0.5f), (float)m.width), 2.0f), 1.0f);
+        const float vy = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn((float)py, 0.5f), (float)m.height), 2.0f), 1.0f);
+        float dxn = __fmul_rn(vx, f.aspect), dyn = vy, dzn = 1.0f;   // :136
+        normalize3(dxn, dyn, dzn);
+        // :137  mat4 * vec4(dir,0) = (m[0]*v0 + m[1]*v1) + (m[2]*v2 + m[3]*0)   (GLM type_mat4x4.inl:561-572)
+        const float* M = f.rotate;
+        const float rx = __fadd_rn(__fadd_rn(__fmul_rn(M[0], dxn), __fmul_rn(M[4], dyn)), __fadd_rn(__fmul_rn(M[8], dzn), __fmul_rn(M[12], 0.0f)));
+        const float ry = __fadd_rn(__fadd_rn(__fmul_rn(M[1], dxn), __fmul_rn(M[5], dyn)), __fadd_rn(__fmul_rn(M[9], dzn), __fmul_rn(M[13], 0.0f)));
+        const float rz = __fadd_rn(__fadd_rn(__fmul_rn(M[2], dxn), __fmul_rn(M[6], dyn)), __fadd_rn(__fmul_rn(M[10], dzn), __fmul_rn(M[14], 0.0f)));
+        r = cast_ray(g, f.cam_pos[0], f.cam_pos[1], f.cam_pos[2], rx, ry, rz, VXRT_RENDER_DIST);   // :139
+        const uint32_t pid = (uint32_t)(py * m.width + px);
+        if (f.view_depth_field == 1) {                               // :143-145
+            const float grey = __fdiv_rn((float)r.steps, 100.0f);
+            o.rgba8[out_index_of(m, px, py)] = pack_rgba8(grey, grey, grey, 1.0f);
+        } else if (r.idx >= 0) {
+            hit = true;                                              // finished by shade_kernel
+        } else {
+            o.rgba8[out_index_of(m, px, py)] = pack_rgba8(0.6f, 0.7f, 0.8f, 1.0f);   // :133
+        }
+        if (o.dbg_hit) {
+            o.dbg_hit[pid] = r.idx;
+            o.dbg_steps[pid] = (uint16_t)(r.steps > 65535 ? 65535 : r.steps);
+            if (!hit) { o.dbg_occl[pid] = 0u; o.dbg_cast[pid] = 0u; }
+        }
+    }
+    // ---- hit compaction: warp ballot -> block prefix -> one global atomic per block -----------
+    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    const unsigned wfetch = __reduce_add_sync(0xffffffffu, (unsigned)r.steps);
+    if (lane == 0) s_warp_hits[warp] = __popc(ballot);
+    __syncthreads();
+    if (lane == 0 && wfetch) atomicAdd(&s_fetches, (unsigned long long)wfetch);
+    if (tid == 0) {
+        unsigned total = 0;
+        #pragma unroll
+        for (int w = 0; w < 8; w++) { const unsigned c = s_warp_hits[w]; s_warp_hits[w] = total; total += c; }
+        s_base = total ? atomicAdd(&o.counters->hit_count, total) : 0u;
+    }
+    __syncthreads();
+    if (hit) {
+        const unsigned pos = s_base + s_warp_hits[warp] + __popc(ballot & ((1u << lane) - 1u));
+        o.hitq[pos] = make_float4(r.hx, r.hy, r.hz, __uint_as_float(((uint32_t)r.voxel & 0x00FFFFFFu) | ((uint32_t)r.normal << 24)));
+        o.hitpix[pos] = (uint32_t)(py * m.width + px);
+    }
+    if (tid == 0 && s_fetches) atomicAdd(&o.counters->fetches_primary, s_fetches);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) shade_kernel(GridView g, const __grid_constant__ FrameParams f,
+                                                    TileMap m, Outputs o) {
+    __shared__ float4 s_light[16];          // compacted active lights (slot order preserved)
+    __shared__ int s_slot[16];
+    __shared__ int s_nactive;
+    __shared__ unsigned long long s_fetches, s_local;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 32) {
+        // fshader.glsl:167: a slot is in the scene iff x,y,z >= 0
+        const bool act = (tid < 16) && f.lights[tid & 15][0] >= 0.0f && f.lights[tid & 15][1] >= 0.0f && f.lights[tid & 15][2] >= 0.0f;
+        const unsigned b = __ballot_sync(0xffffffffu, act);
+        if (act) {
+            const int k = __popc(b & ((1u << lane) - 1u));
+            s_light[k] = make_float4(f.lights[tid][0], f.lights[tid][1], f.lights[tid][2], f.lights[tid][3]);
+            s_slot[k] = tid;
+        }
+        if (tid == 0) { s_nactive = __popc(b); s_fetches = 0ull; s_local = 0ull; }
+    }
+    __syncthreads();
+    const unsigned count = o.counters->hit_count;
+    const unsigned i = blockIdx.x * blockDim.x + tid;
+    unsigned fetches = 0, nlocal = 0;
+    if (i < count) {
+        const float4 rec = o.hitq[i];
+        const uint32_t pid = o.hitpix[i];
+        const uint32_t packed = __float_as_uint(rec.w);
+        float nx, ny, nz;
+        unpack_normal((int)(packed >> 24), nx, ny, nz);
+        const float hx = rec.x, hy = rec.y, hz = rec.z;
+        // :147
+        float lx = __fsub_rn(f.light_pos[0], hx), ly = __fsub_rn(f.light_pos[1], hy), lz = __fsub_rn(f.light_pos[2], hz);
+        normalize3(lx, ly, lz);
+        float multiplier = VXRT_AMBIENT;                             // :149
+        uint32_t occl = 0u, cast = 1u;
+        {   // :154 global-light shadow ray
+            const RayHit s = cast_ray(g, __fadd_rn(hx, __fmul_rn(lx, 0.001f)), __fadd_rn(hy, __fmul_rn(ly, 0.001f)),
+                                      __fadd_rn(hz, __fmul_rn(lz, 0.001f)), lx, ly, lz, VXRT_RENDER_DIST);
+            fetches += (unsigned)s.steps;
+            if (s.idx == -1) multiplier = __fadd_rn(multiplier, __fmul_rn(VXRT_DIFFUSE, max0(dot3(nx, ny, nz, lx, ly, lz))));   // :155
+            else occl |= 1u;
+        }
+        // :159-181.  The reference walks slots 0..15 and tests the overbright clamp at the TOP of every
+        // iteration (active slot or not); walking only the active slots is equivalent when the clamp is also
+        // applied for the inactive iterations that follow the last active slot.
+        const int nact = s_nactive;
+        int last_slot = -1;
+        bool broke = false;
+        for (int k = 0; k < nact; k++) {
+            if (multiplier >= VXRT_MAX_OVERBRIGHT) { multiplier = VXRT_MAX_OVERBRIGHT; broke = true; break; }   // :161-164
+            const float4 L = s_light[k];
+            const int slot = s_slot[k];
+            last_slot = slot;
+            float tx = __fsub_rn(L.x, hx), ty = __fsub_rn(L.y, hy), tz = __fsub_rn(L.z, hz);
+            const float lld = __fsqrt_rn(dot3(tx, ty, tz, tx, ty, tz));                      // :168
+            if (lld <= (float)VXRT_LOCAL_LIGHT_DIST) {                                       // :171
+                normalize3(tx, ty, tz);                                                     // :173
+                cast |= 2u << slot; nlocal++;
+                const RayHit s = cast_ray(g, __fadd_rn(hx, __fmul_rn(tx, 0.001f)), __fadd_rn(hy, __fmul_rn(ty, 0.001f)),
+                                          __fadd_rn(hz, __fmul_rn(tz, 0.001f)), tx, ty, tz, f2i(__fadd_rn(lld, 1.0f)));   // :175
+                fetches += (unsigned)s.steps;
+                if (s.idx == -1) {                                                          // :177
+                    const float fall = __fdiv_rn(__fsub_rn((float)VXRT_LOCAL_LIGHT_DIST, lld), (float)VXRT_LOCAL_LIGHT_DIST);
+                    multiplier = __fadd_rn(multiplier, __fmul_rn(__fmul_rn(L.w, max0(dot3(nx, ny, nz, tx, ty, tz))), fall));
+                } else occl |= 2u << slot;
+            }
+        }
+        if (!broke && last_slot < 15 && multiplier >= VXRT_MAX_OVERBRIGHT) multiplier = VXRT_MAX_OVERBRIGHT;
+        // :184-187
+        const float cr = __fmul_rn(__fdiv_rn((float)((packed >> 16) & 255u), 255.0f), multiplier);
+        const float cg = __fmul_rn(__fdiv_rn((float)((packed >> 8) & 255u), 255.0f), multiplier);
+        const float cb = __fmul_rn(__fdiv_rn((float)(packed & 255u), 255.0f), multiplier);
+        const int px = (int)(pid % (uint32_t)m.width), py = (int)(pid / (uint32_t)m.width);
+        o.rgba8[out_index_of(m, px, py)] = pack_rgba8(cr, cg, cb, 1.0f);
+        if (o.dbg_occl) { o.dbg_occl[pid] = occl; o.dbg_cast[pid] = cast; }
+    }
+    const unsigned wf = __reduce_add_sync(0xffffffffu, fetches), wl = __reduce_add_sync(0xffffffffu, nlocal);
+    if (lane == 0 && wf) { atomicAdd(&s_fetches, (unsigned long long)wf); atomicAdd(&s_local, (unsigned long long)wl); }
+    __syncthreads();
+    if (tid == 0 && s_fetches) { atomicAdd(&o.counters->fetches_shadow, s_fetches); atomicAdd(&o.counters->rays_local, s_local); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// depth field.  Offsets table = computeDepthIndices() render.cpp:66-100, built on the host in the same
+// z,y,x order and uploaded to constant memory.
+constexpr int MAX_DEPTH_OFFSETS = 1536;
+__constant__ float c_off_dist[MAX_DEPTH_OFFSETS];
+__constant__ int c_off_xyz[MAX_DEPTH_OFFSETS];      // (dx+8) | (dy+8)<<8 | (dz+8)<<16
+__constant__ int c_off_count;
+
+struct EditBox {
+    int x0, y0, z0, nx, ny, nz;         // box origin / extents (threads); cells outside the grid are skipped
+    int cx, cy, cz, r2;                 // sphere test x^2+y^2+z^2 < r2 relative to (cx,cy,cz); r2 < 0: whole box
+};
+
+// render.cpp:226-253 for every cell of the box (optionally restricted to the sphere).  In-place like the
+// reference: writers only turn negative values into other negative values, readers only test the sign.
+// Out-of-grid neighbours count as solid (oracle/vxo.c fix_depth_field_n).
+__global__ void __launch_bounds__(256) depth_kernel(int32_t* __restrict__ vox, int w, int h, int d, EditBox b) {
+    const long long tcount = (long long)b.nx * b.ny * b.nz;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tcount) return;
+    const int bx = (int)(t % b.nx), by = (int)((t / b.nx) % b.ny), bz = (int)(t / ((long long)b.nx * b.ny));
+    const int x = b.x0 + bx, y = b.y0 + by, z = b.z0 + bz;
+    if (x < 0 || y < 0 || z < 0 || x >= w || y >= h || z >= d) return;
+    if (b.r2 >= 0) {
+        const int rx = x - b.cx, ry = y - b.cy, rz = z - b.cz;
+        if (!(rx * rx + ry * ry + rz * rz < b.r2)) return;
+    }
+    const int index = x + w * y + w * h * z;                       // w*h*d < 2^31 (the shader indexes with int)
+    if (vox[index] >= 0) return;                                   // :231 only empty cells
+    float nearest = -6.0f;                                          // :227-228
+    const int n = c_off_count;
+    for (int i = 0; i < n; i++) {
+        const int o = c_off_xyz[i];
+        const int xc = x + (o & 255) - 8, yc = y + ((o >> 8) & 255) - 8, zc = z + ((o >> 16) & 255) - 8;
+        const bool oob = (unsigned)xc >= (unsigned)w || (unsigned)yc >= (unsigned)h || (unsigned)zc >= (unsigned)d;
+        const int v = oob ? 0 : vox[xc + w * yc + w * h * zc];
+        const float dist = c_off_dist[i];
+        if (v >= 0 && dist > nearest) nearest = (dist <= -2.0f) ? dist : 0.0f;     // :240-247
+    }
+    if (nearest < 0.0f) vox[index] = __float_as_int(nearest);       // :249-251
+}
+
+// level.cpp:31-42: cells of the lopsided sphere become -1 (destroyVoxel render.cpp:265-271)
+__global__ void carve_kernel(int32_t* __restrict__ vox, int w, int h, int d, EditBox b) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= b.nx * b.ny * b.nz) return;
+    const int x = b.x0 + t % b.nx, y = b.y0 + (t / b.nx) % b.ny, z = b.z0 + t / (b.nx * b.ny);
+    if (x < 0 || y < 0 || z < 0 || x >= w || y >= h || z >= d) return;
+    const int rx = x - b.cx, ry = y - b.cy, rz = z - b.cz;
+    if (rx * rx + ry * ry + rz * rz < b.r2) vox[x + w * y + w * h * z] = -1;
+}
+
+__global__ void set_voxel_kernel(int32_t* vox, long long index, int32_t v) { vox[index] = v; }
+
+// one block per uploaded row: staging holds the rows back to back
+__global__ void scatter_rows_kernel(int32_t* __restrict__ vox, const int32_t* __restrict__ staging,
+                                    const long long* __restrict__ first, int row_len) {
+    const long long dst = first[blockIdx.x];
+    const int32_t* src = staging + (long long)blockIdx.x * row_len;
+    for (int i = threadIdx.x; i < row_len; i += blockDim.x) vox[dst + i] = src[i];
+}
+
+// known-answer hook: n independent castRay calls
+__global__ void cast_rays_kernel(GridView g, int n, const float* __restrict__ starts, const float* __restrict__ dirs,
+                                 const int32_t* __restrict__ dists, int32_t* __restrict__ ret, float* __restrict__ out7) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RayHit r = cast_ray(g, starts[3 * i], starts[3 * i + 1], starts[3 * i + 2], dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], dists[i]);
+    ret[i] = r.idx;
+    float nx, ny, nz;
+    unpack_normal(r.normal, nx, ny, nz);
+    if (r.steps == 0) { nx = 0.0f; ny = 0.0f; nz = 0.0f; }          // hitNormal keeps its initial value when no step ran
+    float* o = out7 + 7 * i;
+    o[0] = r.hx; o[1] = r.hy; o[2] = r.hz; o[3] = nx; o[4] = ny; o[5] = nz; o[6] = (float)r.steps;
+}
+
+// gathered: [world][nlocal][8][32] RGBA8 -> raster [height][width]
+__global__ void assemble_kernel(const uint32_t* __restrict__ gathered, uint32_t* __restrict__ dst, TileMap m) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m.width * m.height) return;
+    const int px = p % m.width, py = p / m.width;
+    const int t = (py / TILE_H) * m.tx + (px / TILE_W);
+    const int rank = t % m.world, local = t / m.world;
+    dst[p] = gathered[((size_t)rank * m.nlocal + local) * TILE_PIX + (py % TILE_H) * TILE_W + (px % TILE_W)];
+}
+
+}  // namespace vxrt

@@ -1,0 +1,568 @@
+// vxrt.cu -- C ABI of libvxrt.so (include/vxrt.h): host side of the B200 per-pixel path.
+// Replaces the GL upload / uniform / draw calls of the reference's src/render.cpp; each entry point cites
+// the reference line it stands in for.  There is NO CPU fallback: without an sm_100 device vxrt_create fails.
+#include "../../include/vxrt.h"
+#include "kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace vxrt;
+
+static_assert(sizeof(FrameParams) == sizeof(vxrt_frame), "FrameParams must mirror vxrt_frame");
+static_assert(VXRT_TILE_W == TILE_W && VXRT_TILE_H == TILE_H, "tile constants");
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(VXRT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+struct vxrt_ctx {
+    vxrt_config cfg{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // grid
+    int32_t* d_vox = nullptr;
+    size_t nvox = 0;
+    bool grid_loaded = false;
+    // frame state
+    vxrt_frame frame{};
+    TileMap map{};
+    // per-frame buffers
+    uint32_t* d_rgba8 = nullptr;
+    size_t out_pixels = 0;              // entries of d_rgba8
+    float4* d_hitq = nullptr;
+    uint32_t* d_hitpix = nullptr;
+    Counters* d_counters = nullptr;
+    int32_t* d_dbg_hit = nullptr;
+    uint16_t* d_dbg_steps = nullptr;
+    uint32_t* d_dbg_occl = nullptr;
+    uint32_t* d_dbg_cast = nullptr;
+    // staging for delta uploads
+    int32_t* h_stage = nullptr;         // pinned
+    int32_t* d_stage = nullptr;
+    long long* h_first = nullptr;       // pinned
+    long long* d_first = nullptr;
+    size_t stage_cap = 0, first_cap = 0;
+    uint8_t* h_frame = nullptr;         // pinned read-back buffer
+    size_t h_frame_cap = 0;
+    bool rendered = false;
+    uint32_t launches = 0;
+};
+
+// ---- helpers -----------------------------------------------------------------------------------
+static TileMap make_map(int width, int height, int rank, int world) {
+    TileMap m;
+    m.width = width; m.height = height;
+    m.tx = (width + TILE_W - 1) / TILE_W; m.ty = (height + TILE_H - 1) / TILE_H;
+    m.ntiles = m.tx * m.ty;
+    m.rank = rank; m.world = world;
+    m.nlocal = (m.ntiles + world - 1) / world;
+    return m;
+}
+
+static GridView grid_view(const vxrt_ctx* c) {
+    GridView g;
+    g.vox = c->d_vox; g.w = c->cfg.grid_w; g.h = c->cfg.grid_h; g.d = c->cfg.grid_d;
+    g.wh = g.w * g.h; g.n = g.w * g.h * g.d;
+    return g;
+}
+
+static void free_frame_buffers(vxrt_ctx* c) {
+    cudaFree(c->d_rgba8); cudaFree(c->d_hitq); cudaFree(c->d_hitpix);
+    cudaFree(c->d_dbg_hit); cudaFree(c->d_dbg_steps); cudaFree(c->d_dbg_occl); cudaFree(c->d_dbg_cast);
+    c->d_rgba8 = nullptr; c->d_hitq = nullptr; c->d_hitpix = nullptr;
+    c->d_dbg_hit = nullptr; c->d_dbg_steps = nullptr; c->d_dbg_occl = nullptr; c->d_dbg_cast = nullptr;
+    if (c->h_frame) cudaFreeHost(c->h_frame);
+    c->h_frame = nullptr; c->h_frame_cap = 0;
+}
+
+static int alloc_frame_buffers(vxrt_ctx* c) {
+    free_frame_buffers(c);
+    c->map = make_map(c->cfg.width, c->cfg.height, c->cfg.rank, c->cfg.world);
+    const size_t npix = (size_t)c->cfg.width * c->cfg.height;
+    const size_t local_pix = (size_t)c->map.nlocal * TILE_PIX;
+    c->out_pixels = (c->cfg.world == 1) ? npix : local_pix;
+    CUDA_TRY(cudaMalloc(&c->d_rgba8, c->out_pixels * 4));
+    CUDA_TRY(cudaMemsetAsync(c->d_rgba8, 0, c->out_pixels * 4, c->stream));
+    CUDA_TRY(cudaMalloc(&c->d_hitq, local_pix * sizeof(float4)));
+    CUDA_TRY(cudaMalloc(&c->d_hitpix, local_pix * 4));
+    if (c->cfg.flags & VXRT_FLAG_DEBUG_OUTPUTS) {
+        CUDA_TRY(cudaMalloc(&c->d_dbg_hit, npix * 4));
+        CUDA_TRY(cudaMalloc(&c->d_dbg_steps, npix * 2));
+        CUDA_TRY(cudaMalloc(&c->d_dbg_occl, npix * 4));
+        CUDA_TRY(cudaMalloc(&c->d_dbg_cast, npix * 4));
+        CUDA_TRY(cudaMemsetAsync(c->d_dbg_hit, 0xFF, npix * 4, c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->d_dbg_steps, 0, npix * 2, c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->d_dbg_occl, 0, npix * 4, c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->d_dbg_cast, 0, npix * 4, c->stream));
+    }
+    c->h_frame_cap = c->out_pixels * 4;
+    CUDA_TRY(cudaMallocHost(&c->h_frame, c->h_frame_cap));
+    c->rendered = false;
+    return VXRT_OK;
+}
+
+// computeDepthIndices() render.cpp:66-100: same z,y,x order, dist = (float)-sqrt((double)k)
+static int upload_depth_offsets() {
+    std::vector<float> dist; std::vector<int> xyz;
+    const int R = 7;
+    for (int zc = -R; zc <= R; zc++)
+        for (int yc = -R; yc <= R; yc++)
+            for (int xc = -R; xc <= R; xc++)
+                if (xc * xc + yc * yc + zc * zc <= R * R) {
+                    const int xd = xc - (xc > 0) + (xc < 0), yd = yc - (yc > 0) + (yc < 0), zd = zc - (zc > 0) + (zc < 0);
+                    const float d = (float)(-std::sqrt((double)(xd * xd + yd * yd + zd * zd)));
+                    if (d <= (float)R) { dist.push_back(d); xyz.push_back((xc + 8) | ((yc + 8) << 8) | ((zc + 8) << 16)); }
+                }
+    const int n = (int)dist.size();
+    if (n > MAX_DEPTH_OFFSETS) return fail(VXRT_ERR_INVALID, "depth offset table overflow");
+    CUDA_TRY(cudaMemcpyToSymbol(c_off_dist, dist.data(), n * sizeof(float)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_off_xyz, xyz.data(), n * sizeof(int)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_off_count, &n, sizeof(int)));
+    return VXRT_OK;
+}
+
+static int ensure_stage(vxrt_ctx* c, size_t elems, size_t rows) {
+    if (elems > c->stage_cap) {
+        if (c->h_stage) cudaFreeHost(c->h_stage);
+        cudaFree(c->d_stage);
+        c->h_stage = nullptr; c->d_stage = nullptr; c->stage_cap = 0;
+        size_t cap = elems < 65536 ? 65536 : elems;
+        CUDA_TRY(cudaMallocHost(&c->h_stage, cap * 4));
+        CUDA_TRY(cudaMalloc(&c->d_stage, cap * 4));
+        c->stage_cap = cap;
+    }
+    if (rows > c->first_cap) {
+        if (c->h_first) cudaFreeHost(c->h_first);
+        cudaFree(c->d_first);
+        c->h_first = nullptr; c->d_first = nullptr; c->first_cap = 0;
+        size_t cap = rows < 4096 ? 4096 : rows;
+        CUDA_TRY(cudaMallocHost(&c->h_first, cap * sizeof(long long)));
+        CUDA_TRY(cudaMalloc(&c->d_first, cap * sizeof(long long)));
+        c->first_cap = cap;
+    }
+    return VXRT_OK;
+}
+
+static int host_index(const vxrt_config& g, int x, int y, int z) {     // getVoxelIndex render.cpp:189-196
+    if (x >= 0 && y >= 0 && z >= 0 && x < g.grid_w && y < g.grid_h && z < g.grid_d)
+        return x + g.grid_w * y + g.grid_w * g.grid_h * z;
+    return -1;
+}
+
+#define CHECK_CTX(c)                                                            \
+    do {                                                                        \
+        if (!(c)) return fail(VXRT_ERR_INVALID, "null context");                \
+        CUDA_TRY(cudaSetDevice((c)->cfg.device));                               \
+    } while (0)
+
+// ---- lifetime ----------------------------------------------------------------------------------
+extern "C" int vxrt_device_available(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return 0; }
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) return 1;
+    }
+    return 0;
+}
+
+extern "C" const char* vxrt_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
+    if (!cfg || !out) return fail(VXRT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->grid_w <= 0 || cfg->grid_h <= 0 || cfg->grid_d <= 0 || cfg->width <= 0 || cfg->height <= 0)
+        return fail(VXRT_ERR_INVALID, "grid and frame extents must be positive");
+    if ((long long)cfg->grid_w * cfg->grid_h * cfg->grid_d > 0x7fffffffLL)
+        return fail(VXRT_ERR_INVALID, "grid too large: the shader indexes voxels with a 32-bit int (fshader.glsl:33-52)");
+    if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world)
+        return fail(VXRT_ERR_INVALID, "bad rank/world");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(VXRT_ERR_NO_DEVICE, "no CUDA device: libvxrt has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(VXRT_ERR_INVALID, "bad device ordinal");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(VXRT_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100: libvxrt is built for sm_100a only");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    vxrt_ctx* c = new vxrt_ctx();
+    c->cfg = *cfg;
+    c->nvox = (size_t)cfg->grid_w * cfg->grid_h * cfg->grid_d;
+    auto bail = [&](int code) { vxrt_destroy(c); return code; };
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaStreamCreate failed"));
+    for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
+    if (cudaMalloc(&c->d_vox, c->nvox * 4) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaMalloc(grid) failed"));
+    if (cudaMalloc(&c->d_counters, sizeof(Counters)) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaMalloc(counters) failed"));
+    int rc = upload_depth_offsets();
+    if (rc != VXRT_OK) return bail(rc);
+    rc = alloc_frame_buffers(c);
+    if (rc != VXRT_OK) return bail(rc);
+    // frame defaults == the reference's globals, main.cpp:26-37
+    memset(&c->frame, 0, sizeof c->frame);
+    c->frame.cam_pos[0] = 195.0f; c->frame.cam_pos[1] = 55.0f; c->frame.cam_pos[2] = 155.0f;
+    c->frame.light_pos[0] = cfg->grid_w / 2.0f; c->frame.light_pos[1] = cfg->grid_w * 3.0f; c->frame.light_pos[2] = cfg->grid_w / 2.0f;
+    c->frame.aspect = (float)cfg->width / cfg->height;
+    for (int i = 0; i < 4; i++) c->frame.rotate[5 * i] = 1.0f;
+    vxrt_init_local_lights(c);
+    *out = c;
+    return VXRT_OK;
+}
+
+extern "C" void vxrt_destroy(vxrt_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_frame_buffers(c);
+    cudaFree(c->d_vox); cudaFree(c->d_counters); cudaFree(c->d_stage); cudaFree(c->d_first);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_first) cudaFreeHost(c->h_first);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// ---- grid --------------------------------------------------------------------------------------
+extern "C" int vxrt_upload_grid(vxrt_ctx* c, const int32_t* voxels, size_t count) {
+    CHECK_CTX(c);
+    if (!voxels || count != c->nvox) return fail(VXRT_ERR_INVALID, "upload_grid: count must equal grid_w*grid_h*grid_d");
+    CUDA_TRY(cudaMemcpyAsync(c->d_vox, voxels, count * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));      // GL semantics: the caller may modify its array on return
+    c->grid_loaded = true;
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_upload_range(vxrt_ctx* c, size_t first, size_t count, const int32_t* src) {
+    CHECK_CTX(c);
+    if (!src) return fail(VXRT_ERR_INVALID, "upload_range: null source");
+    if (first > c->nvox || count > c->nvox - first) return fail(VXRT_ERR_INVALID, "upload_range: range outside the buffer (GL_INVALID_VALUE)");
+    CUDA_TRY(cudaMemcpyAsync(c->d_vox + first, src, count * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+
+// updatePartialGeometry(start,end) render.cpp:204-223 -- same (int) casts, same float loop counters, same
+// start/end swap on linear indices, same "skip the row when its first index is out of bounds".
+extern "C" int vxrt_update_partial(vxrt_ctx* c, const float start_in[3], const float end_in[3],
+                                   const int32_t* host_voxels, int32_t* rows_out) {
+    CHECK_CTX(c);
+    if (!start_in || !end_in || !host_voxels) return fail(VXRT_ERR_INVALID, "update_partial: null argument");
+    float start[3] = {start_in[0], start_in[1], start_in[2]}, end[3] = {end_in[0], end_in[1], end_in[2]};
+    const int startInd = host_index(c->cfg, (int)start[0], (int)start[1], (int)start[2]);
+    const int endInd = host_index(c->cfg, (int)end[0], (int)end[1], (int)end[2]);
+    if (startInd > endInd) for (int k = 0; k < 3; k++) { const float t = start[k]; start[k] = end[k]; end[k] = t; }
+    const int xLength = (int)(end[0] - start[0]) + 1;
+    std::vector<long long> firsts;
+    for (float i = start[2]; i < end[2]; i++)
+        for (float j = start[1]; j < end[1]; j++) {
+            const int offset = host_index(c->cfg, (int)start[0], (int)j, (int)i);
+            if (offset != -1 && xLength > 0 && (size_t)offset + (size_t)xLength <= c->nvox) firsts.push_back(offset);
+        }
+    if (rows_out) *rows_out = (int32_t)firsts.size();
+    if (firsts.empty()) return VXRT_OK;
+    const size_t rows = firsts.size(), elems = rows * (size_t)xLength;
+    int rc = ensure_stage(c, elems, rows);
+    if (rc != VXRT_OK) return rc;
+    for (size_t r = 0; r < rows; r++) {
+        memcpy(c->h_stage + r * xLength, host_voxels + firsts[r], (size_t)xLength * 4);
+        c->h_first[r] = firsts[r];
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_stage, c->h_stage, elems * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_first, c->h_first, rows * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    scatter_rows_kernel<<<(unsigned)rows, 64, 0, c->stream>>>(c->d_vox, c->d_stage, c->d_first, xLength);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));      // staging buffers are reused by the next call
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_download_grid(vxrt_ctx* c, int32_t* out, size_t count) {
+    CHECK_CTX(c);
+    if (!out || count != c->nvox) return fail(VXRT_ERR_INVALID, "download_grid: count must equal grid_w*grid_h*grid_d");
+    CUDA_TRY(cudaMemcpyAsync(out, c->d_vox, count * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_download_box(vxrt_ctx* c, const int32_t lo[3], const int32_t hi[3], int32_t* host_voxels) {
+    CHECK_CTX(c);
+    if (!lo || !hi || !host_voxels) return fail(VXRT_ERR_INVALID, "download_box: null argument");
+    const int W = c->cfg.grid_w, H = c->cfg.grid_h, D = c->cfg.grid_d;
+    const int x0 = lo[0] < 0 ? 0 : lo[0], y0 = lo[1] < 0 ? 0 : lo[1], z0 = lo[2] < 0 ? 0 : lo[2];
+    const int x1 = hi[0] > W ? W : hi[0], y1 = hi[1] > H ? H : hi[1], z1 = hi[2] > D ? D : hi[2];
+    if (x1 <= x0 || y1 <= y0 || z1 <= z0) return VXRT_OK;
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof p);
+    p.srcPtr = make_cudaPitchedPtr(c->d_vox, (size_t)W * 4, (size_t)W, (size_t)H);
+    p.dstPtr = make_cudaPitchedPtr(host_voxels, (size_t)W * 4, (size_t)W, (size_t)H);
+    p.srcPos = make_cudaPos((size_t)x0 * 4, (size_t)y0, (size_t)z0);
+    p.dstPos = p.srcPos;
+    p.extent = make_cudaExtent((size_t)(x1 - x0) * 4, (size_t)(y1 - y0), (size_t)(z1 - z0));
+    p.kind = cudaMemcpyDeviceToHost;
+    CUDA_TRY(cudaMemcpy3DAsync(&p, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_place_voxel(vxrt_ctx* c, int x, int y, int z, int32_t voxel) {      // render.cpp:256-262
+    CHECK_CTX(c);
+    const int index = host_index(c->cfg, x, y, z);
+    if (index >= 0) { set_voxel_kernel<<<1, 1, 0, c->stream>>>(c->d_vox, index, voxel); CUDA_TRY(cudaGetLastError()); }
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_destroy_voxel(vxrt_ctx* c, int x, int y, int z) {                   // render.cpp:265-271
+    CHECK_CTX(c);
+    const int index = host_index(c->cfg, x, y, z);
+    if (x >= 0 && y >= 0 && z >= 0 && index >= 0) { set_voxel_kernel<<<1, 1, 0, c->stream>>>(c->d_vox, index, -1); CUDA_TRY(cudaGetLastError()); }
+    return VXRT_OK;
+}
+
+// removeSphere level.cpp:30-56: loops are [-r, r) per axis, test x^2+y^2+z^2 < r^2; then r += 7>>1 and
+// fixDepthField over that larger lopsided sphere.
+extern "C" int vxrt_edit_remove_sphere(vxrt_ctx* c, int cx, int cy, int cz, int radius) {
+    CHECK_CTX(c);
+    if (radius < 0 || radius > 512) return fail(VXRT_ERR_INVALID, "remove_sphere: radius out of range");
+    if (!c->grid_loaded) return fail(VXRT_ERR_STATE, "remove_sphere before any grid upload");
+    const int W = c->cfg.grid_w, H = c->cfg.grid_h, D = c->cfg.grid_d;
+    if (radius > 0) {
+        EditBox b{cx - radius, cy - radius, cz - radius, 2 * radius, 2 * radius, 2 * radius, cx, cy, cz, radius * radius};
+        const int n = b.nx * b.ny * b.nz;
+        carve_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_vox, W, H, D, b);
+        CUDA_TRY(cudaGetLastError());
+    }
+    const int r2 = radius + (7 >> 1);                                                    // level.cpp:43
+    EditBox f{cx - r2, cy - r2, cz - r2, 2 * r2, 2 * r2, 2 * r2, cx, cy, cz, r2 * r2};
+    const long long n = (long long)f.nx * f.ny * f.nz;
+    depth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_vox, W, H, D, f);
+    CUDA_TRY(cudaGetLastError());
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_build_depth_field(vxrt_ctx* c) {                                     // render.cpp:273-286
+    CHECK_CTX(c);
+    if (!c->grid_loaded) return fail(VXRT_ERR_STATE, "build_depth_field before any grid upload");
+    const int W = c->cfg.grid_w, H = c->cfg.grid_h, D = c->cfg.grid_d;
+    EditBox b{0, 0, 0, W, H, D, 0, 0, 0, -1};
+    const long long n = (long long)W * H * D;
+    depth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_vox, W, H, D, b);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+
+// ---- frame -------------------------------------------------------------------------------------
+extern "C" int vxrt_set_frame(vxrt_ctx* c, const vxrt_frame* f) {                        // render.cpp:289-296
+    if (!c || !f) return fail(VXRT_ERR_INVALID, "null argument");
+    c->frame = *f;
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_get_frame(vxrt_ctx* c, vxrt_frame* out) {
+    if (!c || !out) return fail(VXRT_ERR_INVALID, "null argument");
+    *out = c->frame;
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_init_local_lights(vxrt_ctx* c) {                                     // render.cpp:304-311
+    if (!c) return fail(VXRT_ERR_INVALID, "null context");
+    for (int i = 0; i < VXRT_MAX_LOCAL_LIGHTS; i++) {
+        c->frame.lights[i][0] = -1.0f; c->frame.lights[i][1] = -1.0f; c->frame.lights[i][2] = -1.0f; c->frame.lights[i][3] = 0.0f;
+    }
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_place_local_light(vxrt_ctx* c, float x, float y, float z, float diffuse) {   // render.cpp:375-385
+    if (!c) return fail(VXRT_ERR_INVALID, "null context");
+    for (int i = 0; i < VXRT_MAX_LOCAL_LIGHTS; i++) {
+        float* L = c->frame.lights[i];
+        if (L[0] < 0 || L[1] < 0 || L[2] < 0) { L[0] = x; L[1] = y; L[2] = z; L[3] = diffuse; return i; }
+    }
+    return VXRT_MAX_LOCAL_LIGHTS;
+}
+
+extern "C" int vxrt_resize(vxrt_ctx* c, int width, int height) {                         // render.cpp:404-411
+    CHECK_CTX(c);
+    if (width <= 0 || height <= 0) return fail(VXRT_ERR_INVALID, "resize: extents must be positive");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->cfg.width = width; c->cfg.height = height;
+    c->frame.aspect = (float)width / height;
+    return alloc_frame_buffers(c);
+}
+
+extern "C" int vxrt_render(vxrt_ctx* c) {                                                // main.cpp:59
+    CHECK_CTX(c);
+    if (!c->grid_loaded) return fail(VXRT_ERR_STATE, "render before any grid upload");
+    const GridView g = grid_view(c);
+    FrameParams fp;
+    memcpy(&fp, &c->frame, sizeof fp);
+    Outputs o;
+    o.rgba8 = c->d_rgba8; o.hitq = c->d_hitq; o.hitpix = c->d_hitpix; o.counters = c->d_counters;
+    o.dbg_hit = c->d_dbg_hit; o.dbg_steps = c->d_dbg_steps; o.dbg_occl = c->d_dbg_occl; o.dbg_cast = c->d_dbg_cast;
+    c->launches = 0;
+    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    primary_kernel<<<c->map.nlocal, 256, 0, c->stream>>>(g, fp, c->map, o);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    if (c->frame.view_depth_field != 1) {
+        shade_kernel<<<c->map.nlocal, 256, 0, c->stream>>>(g, fp, c->map, o);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    c->rendered = true;
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_sync(vxrt_ctx* c) {
+    CHECK_CTX(c);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_render_frame_host(vxrt_ctx* c, const vxrt_frame* f, uint8_t* out) {
+    if (!out) return fail(VXRT_ERR_INVALID, "render_frame_host: null output");
+    int rc = vxrt_set_frame(c, f);
+    if (rc != VXRT_OK) return rc;
+    rc = vxrt_render(c);
+    if (rc != VXRT_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->h_frame, c->d_rgba8, c->out_pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(out, c->h_frame, c->out_pixels * 4);
+    return VXRT_OK;
+}
+
+// ---- results -----------------------------------------------------------------------------------
+extern "C" int vxrt_read_rgba8(vxrt_ctx* c, uint8_t* out) {
+    CHECK_CTX(c);
+    if (!out) return fail(VXRT_ERR_INVALID, "read_rgba8: null output");
+    if (!c->rendered) return fail(VXRT_ERR_STATE, "read_rgba8 before render");
+    CUDA_TRY(cudaMemcpyAsync(out, c->d_rgba8, c->out_pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_read_debug(vxrt_ctx* c, int32_t* hit_index, uint16_t* steps, uint32_t* occl_mask, uint32_t* cast_mask) {
+    CHECK_CTX(c);
+    if (!(c->cfg.flags & VXRT_FLAG_DEBUG_OUTPUTS)) return fail(VXRT_ERR_STATE, "read_debug needs VXRT_FLAG_DEBUG_OUTPUTS");
+    if (!c->rendered) return fail(VXRT_ERR_STATE, "read_debug before render");
+    const size_t npix = (size_t)c->cfg.width * c->cfg.height;
+    if (hit_index) CUDA_TRY(cudaMemcpyAsync(hit_index, c->d_dbg_hit, npix * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (steps) CUDA_TRY(cudaMemcpyAsync(steps, c->d_dbg_steps, npix * 2, cudaMemcpyDeviceToHost, c->stream));
+    if (occl_mask) CUDA_TRY(cudaMemcpyAsync(occl_mask, c->d_dbg_occl, npix * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (cast_mask) CUDA_TRY(cudaMemcpyAsync(cast_mask, c->d_dbg_cast, npix * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_get_stats(vxrt_ctx* c, vxrt_stats* out) {
+    CHECK_CTX(c);
+    if (!out) return fail(VXRT_ERR_INVALID, "get_stats: null output");
+    if (!c->rendered) return fail(VXRT_ERR_STATE, "get_stats before render");
+    Counters h;
+    CUDA_TRY(cudaMemcpyAsync(&h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memset(out, 0, sizeof *out);
+    // pixels this context rendered (padding tiles and clipped pixels excluded)
+    uint64_t pix = 0;
+    for (int j = 0; j < c->map.nlocal; j++) {
+        const int t = j * c->map.world + c->map.rank;
+        if (t >= c->map.ntiles) break;
+        const int x0 = (t % c->map.tx) * TILE_W, y0 = (t / c->map.tx) * TILE_H;
+        const int w = (c->map.width - x0 < TILE_W) ? c->map.width - x0 : TILE_W;
+        const int hgt = (c->map.height - y0 < TILE_H) ? c->map.height - y0 : TILE_H;
+        pix += (uint64_t)w * hgt;
+    }
+    out->rays_primary = pix;
+    out->hit_pixels = h.hit_count;
+    out->rays_global = (c->frame.view_depth_field == 1) ? 0 : h.hit_count;
+    out->rays_local = h.rays_local;
+    out->fetches = h.fetches_primary + h.fetches_shadow;
+    out->fetches_primary = h.fetches_primary;
+    CUDA_TRY(cudaEventElapsedTime(&out->ms_primary, c->ev[0], c->ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&out->ms_shadow, c->ev[1], c->ev[2]));
+    CUDA_TRY(cudaEventElapsedTime(&out->ms_total, c->ev[0], c->ev[2]));
+    out->kernel_launches = c->launches;
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_cast_rays(vxrt_ctx* c, int32_t n, const float* starts, const float* dirs, const int32_t* dists,
+                              int32_t* ret, float* out7) {
+    CHECK_CTX(c);
+    if (n < 0 || (n > 0 && (!starts || !dirs || !dists || !ret || !out7))) return fail(VXRT_ERR_INVALID, "cast_rays: bad argument");
+    if (!c->grid_loaded) return fail(VXRT_ERR_STATE, "cast_rays before any grid upload");
+    if (n == 0) return VXRT_OK;
+    float *d_s = nullptr, *d_d = nullptr, *d_o = nullptr; int32_t *d_n = nullptr, *d_r = nullptr;
+    auto cleanup = [&]() { cudaFree(d_s); cudaFree(d_d); cudaFree(d_o); cudaFree(d_n); cudaFree(d_r); };
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&d_s, (size_t)n * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&d_d, (size_t)n * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&d_o, (size_t)n * 28);
+    if (e == cudaSuccess) e = cudaMalloc(&d_n, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_r, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_s, starts, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dirs, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, dists, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        cast_rays_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(grid_view(c), n, d_s, d_d, d_n, d_r, d_o);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ret, d_r, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out7, d_o, (size_t)n * 28, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(VXRT_ERR_CUDA, std::string("cast_rays: ") + cudaGetErrorString(e));
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_write_ppm(vxrt_ctx* c, const char* path) {
+    CHECK_CTX(c);
+    if (!path) return fail(VXRT_ERR_INVALID, "write_ppm: null path");
+    if (c->cfg.world != 1) return fail(VXRT_ERR_STATE, "write_ppm needs a whole-frame context (world == 1)");
+    const int W = c->cfg.width, H = c->cfg.height;
+    std::vector<uint8_t> rgba((size_t)W * H * 4);
+    int rc = vxrt_read_rgba8(c, rgba.data());
+    if (rc != VXRT_OK) return rc;
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return fail(VXRT_ERR_IO, std::string("cannot open ") + path);
+    fprintf(fp, "P6\n%d %d\n255\n", W, H);
+    std::vector<uint8_t> row((size_t)W * 3);
+    for (int y = H - 1; y >= 0; y--) {                   // GL rows are bottom-up
+        for (int x = 0; x < W; x++) for (int k = 0; k < 3; k++) row[3 * x + k] = rgba[4 * ((size_t)y * W + x) + k];
+        fwrite(row.data(), 1, row.size(), fp);
+    }
+    fclose(fp);
+    return VXRT_OK;
+}
+
+// ---- multi-GPU plumbing --------------------------------------------------------------------------
+extern "C" size_t vxrt_local_tiles(vxrt_ctx* c) { return c ? (size_t)c->map.nlocal : 0; }
+extern "C" size_t vxrt_local_bytes(vxrt_ctx* c) { return c ? (size_t)c->map.nlocal * TILE_PIX * 4 : 0; }
+extern "C" void* vxrt_device_rgba8(vxrt_ctx* c) { return c ? (void*)c->d_rgba8 : nullptr; }
+extern "C" void* vxrt_stream(vxrt_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+extern "C" int vxrt_assemble_tiles(vxrt_ctx* c, const void* gathered, void* dst, void* stream) {
+    CHECK_CTX(c);
+    if (!gathered || !dst) return fail(VXRT_ERR_INVALID, "assemble_tiles: null pointer");
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    const int n = c->cfg.width * c->cfg.height;
+    TileMap m = c->map;
+    assemble_kernel<<<(n + 255) / 256, 256, 0, s>>>((const uint32_t*)gathered, (uint32_t*)dst, m);
+    CUDA_TRY(cudaGetLastError());
+    return VXRT_OK;
+}
