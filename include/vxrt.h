@@ -78,6 +78,8 @@ void vxrt_destroy(vxrt_ctx* ctx);
 const char* vxrt_last_error(void);
 /* 1 iff a device of compute capability 10.x is present */
 int vxrt_device_available(void);
+/* FNV-1a-64 of a host buffer (grid fingerprints) */
+uint64_t vxrt_fnv1a64(const void* data, size_t nbytes);
 
 /* ---- grid ------------------------------------------------------------------------------------- */
 /* updateGeometry() render.cpp:199-202 / glBufferData render.cpp:368: whole grid, count must equal w*h*d */
@@ -103,6 +105,18 @@ int vxrt_destroy_voxel(vxrt_ctx* ctx, int x, int y, int z);
 int vxrt_edit_remove_sphere(vxrt_ctx* ctx, int cx, int cy, int cz, int radius);
 /* computeDepthField sweep over the whole grid, render.cpp:226-253,273-286 (out-of-grid neighbours = solid) */
 int vxrt_build_depth_field(vxrt_ctx* ctx);
+
+/* ---- procedural levels, generated on the device ------------------------------------------------- */
+/* the reference's default level: fill -1 (render.cpp:349-352) + initVoxels() (level.cpp:82-138) incl. its
+   origin-carving quirk (level.cpp:11,64); no depth field yet (the reference builds it in background threads) */
+int vxrt_generate_default_level(vxrt_ctx* ctx);
+/* synthetic terrain of config C4: integer-only 5-octave value-noise height field
+   (lattice hash = splitmix64(seed ^ ix*73856093 ^ iz*19349663 ^ octave*83492791) >> 48), the reference's
+   stone / dirt(8) / grass(3) bands and colour jitter relative to the surface, the reference's trees
+   (x%30==0, z%25==0) standing on it.  No depth field. */
+int vxrt_generate_terrain(vxrt_ctx* ctx, uint64_t seed);
+/* surface height of that terrain at (x,z) for a grid of height grid_h (host-side, for camera placement) */
+int vxrt_terrain_height(uint64_t seed, int x, int z, int grid_h);
 
 /* ---- frame ------------------------------------------------------------------------------------ */
 /* updateUniforms() render.cpp:289-296 */
@@ -132,6 +146,9 @@ int vxrt_get_stats(vxrt_ctx* ctx, vxrt_stats* out);
    starts/dirs n*3 floats, dists n ints); ret[n] = return value, out7[n*7] = hitPos[3] hitNormal[3] stepCount */
 int vxrt_cast_rays(vxrt_ctx* ctx, int32_t n, const float* starts, const float* dirs, const int32_t* dists,
                    int32_t* ret, float* out7);
+/* device self-test of the kernels' exact division-by-ray-direction (ray.cuh div_by) against IEEE division on n
+   pseudo-random operand pairs inside its documented domain; *mismatches must come back 0 */
+int vxrt_selftest_division(vxrt_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches);
 /* binary PPM (P6), rows flipped so the image is upright */
 int vxrt_write_ppm(vxrt_ctx* ctx, const char* path);
 

@@ -72,6 +72,11 @@ def test_cast_ray_known_answers(vx, oracle, golden, ren):
     assert h64(oracle, out7) == g["out7_fnv"]
 
 
+def test_fast_division_matches_ieee(vx, ren):
+    """ray.cuh div_by (hoisted reciprocal + 3 FFMA) == __fdiv_rn on 2^31 random operand pairs of its domain"""
+    assert ren.selftestDivision(1 << 31, seed=12345) == 0
+
+
 @pytest.mark.parametrize("cfg", [("C1", 1280, 720), ("C2", 1920, 1080), ("C3i", 1920, 1080), ("C3ii_pitched", 1280, 720)])
 def test_baseline_configs_vs_oracle(vx, oracle, default_level, ren, cfg):
     name, W, H = cfg
@@ -153,6 +158,26 @@ def test_other_grid_shapes(vx, oracle, dims):
 
 
 # ---- grid plumbing: uploads, edits, depth field ------------------------------------------------------
+def test_device_level_generator_matches_reference_level(vx, oracle, golden):
+    """initVoxels() (level.cpp:82-138, incl. the origin-carving quirk) generated on the device, then the device
+    depth-field sweep: both reference fingerprints"""
+    with vx.Renderer(grid=gc.DIMS, width=32, height=8) as r:
+        r.initVoxels()
+        assert h64(oracle, r.downloadGrid()) == golden["ref_host"]["nodepth"]["fnv"] == "2f8d49bd81549f5a"
+        r.buildDepthField()
+        assert h64(oracle, r.downloadGrid()) == golden["ref_host"]["depth"]["fnv"]
+
+
+def test_device_terrain_generator_matches_host_statement(vx):
+    import terrain_port
+    dims = (160, 128, 96)
+    with vx.Renderer(grid=dims, width=32, height=8) as r:
+        r.generateTerrain(seed=0x5EED)
+        got = r.downloadGrid()
+        assert np.array_equal(got, terrain_port.generate(dims, 0x5EED))
+        assert r.terrainHeight(17, 33) == terrain_port.height(0x5EED, 17, 33, dims[1])
+
+
 def test_upload_download_round_trip_and_ranges(vx, oracle, default_level):
     with vx.Renderer(grid=gc.DIMS, width=32, height=8) as r:
         r.updateGeometry(default_level)

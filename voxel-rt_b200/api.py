@@ -50,6 +50,7 @@ _SIGNATURES = {
     "vxrt_destroy": (None, [C.c_void_p]),
     "vxrt_last_error": (C.c_char_p, []),
     "vxrt_device_available": (C.c_int, []),
+    "vxrt_fnv1a64": (C.c_uint64, [C.c_void_p, C.c_size_t]),
     "vxrt_upload_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "vxrt_upload_range": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     "vxrt_update_partial": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.POINTER(C.c_int32)]),
@@ -59,6 +60,9 @@ _SIGNATURES = {
     "vxrt_destroy_voxel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "vxrt_edit_remove_sphere": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "vxrt_build_depth_field": (C.c_int, [C.c_void_p]),
+    "vxrt_generate_default_level": (C.c_int, [C.c_void_p]),
+    "vxrt_generate_terrain": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "vxrt_terrain_height": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_int]),
     "vxrt_set_frame": (C.c_int, [C.c_void_p, C.POINTER(Frame)]),
     "vxrt_init_local_lights": (C.c_int, [C.c_void_p]),
     "vxrt_place_local_light": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]),
@@ -71,6 +75,7 @@ _SIGNATURES = {
     "vxrt_read_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vxrt_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "vxrt_cast_rays": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vxrt_selftest_division": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "vxrt_write_ppm": (C.c_int, [C.c_void_p, C.c_char_p]),
     "vxrt_local_tiles": (C.c_size_t, [C.c_void_p]),
     "vxrt_local_bytes": (C.c_size_t, [C.c_void_p]),
@@ -215,6 +220,17 @@ class Renderer:
         """computeDepthField sweep (render.cpp:273-286) on the device."""
         self._check(self.lib.vxrt_build_depth_field(self._h))
 
+    def initVoxels(self):
+        """render.cpp:349-352 + level.cpp:82-138 generated on the device (no depth field)."""
+        self._check(self.lib.vxrt_generate_default_level(self._h))
+
+    def generateTerrain(self, seed=0x5EED):
+        """config C4's synthetic terrain, generated on the device (no depth field)."""
+        self._check(self.lib.vxrt_generate_terrain(self._h, int(seed)))
+
+    def terrainHeight(self, x, z, seed=0x5EED):
+        return int(self.lib.vxrt_terrain_height(int(seed), int(x), int(z), self.grid[1]))
+
     def downloadGrid(self):
         out = np.empty(self.nvox, np.int32)
         self._check(self.lib.vxrt_download_grid(self._h, _vp(out), out.size))
@@ -294,6 +310,11 @@ class Renderer:
         out7 = np.zeros((n, 7), np.float32)
         self._check(self.lib.vxrt_cast_rays(self._h, n, _vp(starts), _vp(dirs), _vp(dists), _vp(ret), _vp(out7)))
         return ret, out7
+
+    def selftestDivision(self, n, seed=1):
+        bad = C.c_uint64(0)
+        self._check(self.lib.vxrt_selftest_division(self._h, int(n), int(seed), C.byref(bad)))
+        return int(bad.value)
 
     def writePPM(self, path):
         self._check(self.lib.vxrt_write_ppm(self._h, str(path).encode()))

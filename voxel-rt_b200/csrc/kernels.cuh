@@ -276,6 +276,30 @@ __global__ void cast_rays_kernel(GridView g, int n, const float* __restrict__ st
     o[0] = r.hx; o[1] = r.hy; o[2] = r.hz; o[3] = nx; o[4] = ny; o[5] = nz; o[6] = (float)r.steps;
 }
 
+__host__ __device__ inline uint64_t splitmix64(uint64_t x);
+// self-test of ray.cuh's exact division: random (a, b) inside the fast domain (|b| in [2^-40, 2], |a| in
+// [2^-40, 2^31], all exponents / mantissas / signs), div_by(a, b, refined_rcp(b)) against IEEE __fdiv_rn(a, b)
+__global__ void division_selftest_kernel(unsigned long long n, unsigned long long seed, unsigned long long* mismatches) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long h1 = splitmix64(seed + 2 * i), h2 = splitmix64(seed + 2 * i + 1);
+        // exponent of b in [-40, 0], of a in [-40, 30]; full 23-bit mantissas; half of the a's are "near-integer minus
+        // position" style values (difference of an integer and a float of magnitude < 2^10), like the kernel's dividends
+        const int eb = 127 - 40 + (int)((h1 >> 40) % 41), ea = 127 - 40 + (int)((h2 >> 40) % 71);
+        const float b = __uint_as_float((unsigned)((h1 >> 63) << 31) | ((unsigned)eb << 23) | (unsigned)(h1 & 0x7FFFFF));
+        float a = __uint_as_float((unsigned)((h2 >> 63) << 31) | ((unsigned)ea << 23) | (unsigned)(h2 & 0x7FFFFF));
+        if (i & 1) {
+            const float pos = __uint_as_float((unsigned)((127 + (h2 >> 50) % 10) << 23) | (unsigned)(h2 & 0x7FFFFF));
+            a = __fsub_rn((float)(__float2int_rz(pos) + (int)((h1 >> 33) & 1)), pos);
+            if (!(fabsf(a) >= VXRT_DIV_LO)) continue;
+        }
+        const float q = div_by(a, b, refined_rcp(b)), want = __fdiv_rn(a, b);
+        if (__float_as_uint(q) != __float_as_uint(want)) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // gathered: [world][nlocal][8][32] RGBA8 -> raster [height][width]
 __global__ void assemble_kernel(const uint32_t* __restrict__ gathered, uint32_t* __restrict__ dst, TileMap m) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,6 +308,115 @@ __global__ void assemble_kernel(const uint32_t* __restrict__ gathered, uint32_t*
     const int t = (py / TILE_H) * m.tx + (px / TILE_W);
     const int rank = t % m.world, local = t / m.world;
     dst[p] = gathered[((size_t)rank * m.nlocal + local) * TILE_PIX + (py % TILE_H) * TILE_W + (px % TILE_W)];
+}
+
+}  // namespace vxrt
+
+// ================================================================================================
+// Procedural levels generated on the device: the reference's default level
+// (level.cpp:82-138, incl. its origin-carving quirk) and the synthetic terrain of config C4.
+namespace vxrt {
+
+__device__ __forceinline__ int slab_voxel(int x, int y, int z, int s_stone, int s_dirt, int s_grass) {
+    const int cv = 5 * ((x + y + z) % 3);                            // level.cpp:89
+    if (y <= s_stone) return ((90 + cv) << 16) | ((90 + cv) << 8) | (90 + cv);        // level.cpp:94-103
+    if (y <= s_dirt) return ((120 + cv) << 16) | ((100 + cv) << 8);                   // level.cpp:105-114
+    if (y <= s_grass) return (10 << 16) | ((130 + cv) << 8) | 10;                     // level.cpp:116-125
+    return -1;                                                       // destroyVoxel level.cpp:91
+}
+
+// level.cpp:85-128: stone y<=25, dirt y<=33, grass y<=36
+__global__ void default_slabs_kernel(int32_t* __restrict__ vox, int w, int h, int d) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)w * h * d) return;
+    const int x = (int)(i % w), y = (int)((i / w) % h), z = (int)(i / ((long long)w * h));
+    vox[i] = slab_voxel(x, y, z, 25, 33, 36);
+}
+
+__device__ __forceinline__ void dev_place(int32_t* vox, int w, int h, int d, int x, int y, int z, int v) {   // render.cpp:256-262
+    if (x >= 0 && y >= 0 && z >= 0 && x < w && y < h && z < d) vox[x + w * y + w * h * z] = v;
+}
+__device__ __forceinline__ void dev_destroy(int32_t* vox, int w, int h, int d, int x, int y, int z) {        // render.cpp:265-271
+    if (x >= 0 && y >= 0 && z >= 0 && x < w && y < h && z < d) vox[x + w * y + w * h * z] = -1;
+}
+
+// One block per tree (level.cpp:130-137): placeTrunk (level.cpp:59-79) then placeBush (level.cpp:4-27).
+// `relative_destroy` reproduces the reference calling destroyVoxel with sphere-RELATIVE coordinates
+// (level.cpp:11,64), which carves a small cavity at the world origin; trees never overlap each other or
+// that cavity, so blocks are independent.  base_y < 0: take the trunk base from `surface` (terrain mode).
+__global__ void trees_kernel(int32_t* __restrict__ vox, int w, int h, int d, int ntx, int base_y,
+                             const int* __restrict__ surface, int relative_destroy) {
+    const int tx = blockIdx.x % ntx, tz = blockIdx.x / ntx;
+    const int x = 30 * (tx + 1), z = 25 * (tz + 1);                  // x % 30 == 0, z % 25 == 0, both >= 10
+    if (x >= w - 10 || z >= d - 10) return;
+    const int by = base_y >= 0 ? base_y : surface[x + (long long)w * z];
+    {   // placeTrunk(ivec3(x + 1 + z % 7, 36, z), (128,100,15), 6): rel x,z in [-2,1), y in [0,6)
+        const int px = x + 1 + z % 7, py = by, pz = z;
+        for (int t = threadIdx.x; t < 3 * 6 * 3; t += blockDim.x) {
+            const int rx = t % 3 - 2, ry = (t / 3) % 6, rz = t / 18 - 2;
+            if (rx + px < w && ry + py < h && rz + pz < d) {
+                if (relative_destroy) dev_destroy(vox, w, h, d, rx, ry, rz);
+                const int m = ((rx + rz) % 2) * 10;                  // C remainder keeps the sign
+                dev_place(vox, w, h, d, rx + px, ry + py, rz + pz, ((128 - m) << 16) | ((100 - m) << 8) | 15);
+            }
+        }
+    }
+    __syncthreads();                                                 // the bush overwrites trunk cells it overlaps
+    {   // placeBush(ivec3(x + z % 7, 36 + 10, z), (15,128,15), 6)
+        const int px = x + z % 7, py = by + 10, pz = z;
+        for (int t = threadIdx.x; t < 12 * 12 * 12; t += blockDim.x) {
+            const int rx = t % 12 - 6, ry = (t / 12) % 12 - 6, rz = t / 144 - 6;
+            if (rx + px < w && ry + py < h && rz + pz < d && rx + px >= 0 && ry + py >= 0 && rz + pz >= 0 &&
+                rx * rx + ry * ry + rz * rz < 36) {
+                if (relative_destroy) dev_destroy(vox, w, h, d, rx, ry, rz);
+                dev_place(vox, w, h, d, rx + px, ry + py, rz + pz, (15 << 16) | ((128 - ((rx + ry + rz) % 3) * 20) << 8) | 15);
+            }
+        }
+    }
+}
+
+// ---- synthetic terrain (config C4), integer-only so that any implementation reproduces it bit for bit ----
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__host__ __device__ inline uint32_t lattice16(uint64_t seed, int ix, int iz, int oct) {
+    const uint64_t k = seed ^ ((uint64_t)(uint32_t)ix * 73856093ull) ^ ((uint64_t)(uint32_t)iz * 19349663ull) ^ ((uint64_t)oct * 83492791ull);
+    return (uint32_t)(splitmix64(k) >> 48);                          // 16-bit lattice value
+}
+// 5 octaves of bilinear value noise, cell sizes 256,128,64,32,16, weights 1/2,1/4,...; result in [0, 65535]
+__host__ __device__ inline uint32_t fbm16(uint64_t seed, int x, int z) {
+    uint64_t acc = 0;
+    for (int o = 0; o < 5; o++) {
+        const int S = 256 >> o;
+        const int ix = x / S, iz = z / S, fx = x % S, fz = z % S;
+        const uint64_t v00 = lattice16(seed, ix, iz, o), v10 = lattice16(seed, ix + 1, iz, o);
+        const uint64_t v01 = lattice16(seed, ix, iz + 1, o), v11 = lattice16(seed, ix + 1, iz + 1, o);
+        const uint64_t top = v00 * (uint64_t)(S - fx) + v10 * (uint64_t)fx, bot = v01 * (uint64_t)(S - fx) + v11 * (uint64_t)fx;
+        const uint64_t v = (top * (uint64_t)(S - fz) + bot * (uint64_t)fz) / ((uint64_t)S * S);
+        acc += v >> (o + 1);
+    }
+    return (uint32_t)(acc > 65535 ? 65535 : acc);
+}
+// surface height: h/4 + fbm * (h*3/8) / 65536  -> for h = 1024: [256, 640)
+__host__ __device__ inline int terrain_height(uint64_t seed, int x, int z, int h) {
+    return h / 4 + (int)(((uint64_t)fbm16(seed, x, z) * (uint64_t)(h * 3 / 8)) >> 16);
+}
+
+__global__ void terrain_surface_kernel(int* __restrict__ surface, int w, int h, int d, uint64_t seed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * d) return;
+    surface[i] = terrain_height(seed, i % w, i / w, h);
+}
+// material bands relative to the surface s: stone y <= s-11, dirt y <= s-3 (8 layers), grass y <= s (3 layers)
+__global__ void terrain_slabs_kernel(int32_t* __restrict__ vox, const int* __restrict__ surface, int w, int h, int d) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)w * h * d) return;
+    const int x = (int)(i % w), y = (int)((i / w) % h), z = (int)(i / ((long long)w * h));
+    const int s = surface[x + (long long)w * z];
+    vox[i] = slab_voxel(x, y, z, s - 11, s - 3, s);
 }
 
 }  // namespace vxrt

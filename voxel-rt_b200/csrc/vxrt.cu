@@ -180,6 +180,13 @@ extern "C" int vxrt_device_available(void) {
 
 extern "C" const char* vxrt_last_error(void) { return g_last_error.c_str(); }
 
+extern "C" uint64_t vxrt_fnv1a64(const void* data, size_t nbytes) {
+    const uint8_t* p = (const uint8_t*)data;
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < nbytes; i++) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
 extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     if (!cfg || !out) return fail(VXRT_ERR_INVALID, "null argument");
     *out = nullptr;
@@ -364,6 +371,51 @@ extern "C" int vxrt_build_depth_field(vxrt_ctx* c) {                            
     return VXRT_OK;
 }
 
+// ---- procedural levels ---------------------------------------------------------------------------
+static int launch_trees(vxrt_ctx* c, int base_y, const int* surface, int relative_destroy) {
+    const int W = c->cfg.grid_w, H = c->cfg.grid_h, D = c->cfg.grid_d;
+    const int ntx = (W - 11) / 30, ntz = (D - 11) / 25;             // trees at x = 30..,  z = 25.. below w-10 / d-10
+    if (ntx > 0 && ntz > 0) {
+        trees_kernel<<<ntx * ntz, 128, 0, c->stream>>>(c->d_vox, W, H, D, ntx, base_y, surface, relative_destroy);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return VXRT_OK;
+}
+
+// render.cpp:349-352 (fill -1) + initVoxels() level.cpp:82-138, generalised from 512x96x512 to the context's grid
+extern "C" int vxrt_generate_default_level(vxrt_ctx* c) {
+    CHECK_CTX(c);
+    const long long n = (long long)c->nvox;
+    default_slabs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_vox, c->cfg.grid_w, c->cfg.grid_h, c->cfg.grid_d);
+    CUDA_TRY(cudaGetLastError());
+    int rc = launch_trees(c, 36, nullptr, 1);
+    if (rc != VXRT_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->grid_loaded = true;
+    return VXRT_OK;
+}
+
+// config C4: integer fbm height field, the reference's material bands relative to the surface,
+// the reference's trees standing on the surface.  No depth field (call vxrt_build_depth_field next).
+extern "C" int vxrt_generate_terrain(vxrt_ctx* c, uint64_t seed) {
+    CHECK_CTX(c);
+    const int W = c->cfg.grid_w, H = c->cfg.grid_h, D = c->cfg.grid_d;
+    int* d_surface = nullptr;
+    CUDA_TRY(cudaMalloc(&d_surface, (size_t)W * D * sizeof(int)));
+    terrain_surface_kernel<<<(W * D + 255) / 256, 256, 0, c->stream>>>(d_surface, W, H, D, seed);
+    const long long n = (long long)c->nvox;
+    terrain_slabs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_vox, d_surface, W, H, D);
+    cudaError_t e = cudaGetLastError();
+    int rc = (e == cudaSuccess) ? launch_trees(c, -1, d_surface, 0) : fail(VXRT_ERR_CUDA, cudaGetErrorString(e));
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_surface);
+    if (rc != VXRT_OK) return rc;
+    c->grid_loaded = true;
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_terrain_height(uint64_t seed, int x, int z, int grid_h) { return terrain_height(seed, x, z, grid_h); }
+
 // ---- frame -------------------------------------------------------------------------------------
 extern "C" int vxrt_set_frame(vxrt_ctx* c, const vxrt_frame* f) {                        // render.cpp:289-296
     if (!c || !f) return fail(VXRT_ERR_INVALID, "null argument");
@@ -527,6 +579,23 @@ extern "C" int vxrt_cast_rays(vxrt_ctx* c, int32_t n, const float* starts, const
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cleanup();
     if (e != cudaSuccess) return fail(VXRT_ERR_CUDA, std::string("cast_rays: ") + cudaGetErrorString(e));
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_selftest_division(vxrt_ctx* c, uint64_t n, uint64_t seed, uint64_t* mismatches) {
+    CHECK_CTX(c);
+    if (!mismatches) return fail(VXRT_ERR_INVALID, "selftest_division: null output");
+    unsigned long long* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 8));
+    cudaMemsetAsync(d, 0, 8, c->stream);
+    division_selftest_kernel<<<148 * 8, 256, 0, c->stream>>>(n, seed, d);
+    unsigned long long h = 0;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(VXRT_ERR_CUDA, std::string("selftest_division: ") + cudaGetErrorString(e));
+    *mismatches = h;
     return VXRT_OK;
 }
 

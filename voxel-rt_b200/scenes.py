@@ -59,6 +59,18 @@ def edit_centres(n, seed=12345):
     return c
 
 
+def fnv1a64(a):
+    """FNV-1a-64 of an array's bytes (the grid fingerprints of SURVEY.md 8c); vectorised per byte position is not
+    possible for FNV, so this walks 1 MiB chunks through a small C-speed loop via int.from_bytes-free arithmetic."""
+    import ctypes
+    data = np.ascontiguousarray(a).view(np.uint8).ravel()
+    h = 1469598103934665603
+    # pure Python would take minutes for 96 MiB; use the product library's helper when loaded
+    from . import api
+    lib = api.load_library()
+    return int(lib.vxrt_fnv1a64(data.ctypes.data_as(ctypes.c_void_p), data.size))
+
+
 # ---- ray / byte accounting (SURVEY.md 8d) -----------------------------------------------------------
 def algorithmic_bytes(stats, width, height):
     """4 B x voxel fetches + 4 B x hit pixels (colour, counted once) + 4 B x pixels (RGBA8 store) + 360 B uniforms."""
