@@ -235,7 +235,7 @@ def run_b200(args):
     value = rays / (ms_per_step * 1e-3) / 1e6                    # Mrays/s, whole job
 
     # ---- e2e: the public C-ABI call with HOST buffers (frame params in, RGBA8 frame out), wall clock ----
-    host_out = np.empty(ren.out_shape(), np.uint8)
+    host_out = ren.hostFrameBuffer()                              # page-locked (vxrt_host_alloc)
     final_host = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() if world > 1 else None
 
     def step_e2e():

@@ -78,6 +78,10 @@ void vxrt_destroy(vxrt_ctx* ctx);
 const char* vxrt_last_error(void);
 /* 1 iff a device of compute capability 10.x is present */
 int vxrt_device_available(void);
+/* page-locked host memory for frame read-back (vxrt_render_frame_host / vxrt_read_rgba8 copy straight into it);
+   any other host pointer works too, through an internal staging buffer */
+void* vxrt_host_alloc(size_t nbytes);
+void vxrt_host_free(void* p);
 /* FNV-1a-64 of a host buffer (grid fingerprints) */
 uint64_t vxrt_fnv1a64(const void* data, size_t nbytes);
 

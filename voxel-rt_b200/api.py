@@ -50,6 +50,8 @@ _SIGNATURES = {
     "vxrt_destroy": (None, [C.c_void_p]),
     "vxrt_last_error": (C.c_char_p, []),
     "vxrt_device_available": (C.c_int, []),
+    "vxrt_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "vxrt_host_free": (None, [C.c_void_p]),
     "vxrt_fnv1a64": (C.c_uint64, [C.c_void_p, C.c_size_t]),
     "vxrt_upload_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "vxrt_upload_range": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
@@ -144,6 +146,7 @@ class Renderer:
                      FLAG_DEBUG_OUTPUTS if debug else 0)
         h = C.c_void_p()
         self._h = None
+        self._pinned = []
         self._check(self.lib.vxrt_create(C.byref(cfg), C.byref(h)))
         self._h = h
 
@@ -157,6 +160,9 @@ class Renderer:
         if self._h is not None:
             self.lib.vxrt_destroy(self._h)
             self._h = None
+            for p in self._pinned:
+                self.lib.vxrt_host_free(p)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -273,6 +279,16 @@ class Renderer:
 
     def out_shape(self):
         return (self.height, self.width, 4) if self.world == 1 else (self.local_bytes() // (TILE_W * TILE_H * 4), TILE_H, TILE_W, 4)
+
+    def hostFrameBuffer(self):
+        """page-locked numpy frame buffer (vxrt_host_alloc) for renderFrameHost; freed with the renderer"""
+        shape = self.out_shape()
+        n = int(np.prod(shape))
+        p = self.lib.vxrt_host_alloc(n)
+        if not p:
+            raise VxrtError("vxrt_host_alloc failed")
+        self._pinned.append(p)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n,)).reshape(shape)
 
     def renderFrameHost(self, frame, out=None):
         """updateUniforms + draw + read-back to host memory in one call (the end-to-end path)."""

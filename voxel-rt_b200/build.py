@@ -18,6 +18,23 @@ NVCC_FLAGS = [
 ]
 
 
+HOST_SRCS = [os.path.join(HERE, "csrc", "host", "vxrt_render.cpp"), os.path.join(HERE, "csrc", "host", "vxrt_headless.cpp")]
+HOST_DEPS = HOST_SRCS + [os.path.join(HERE, "csrc", "host", "vxrt_render.hpp")]
+HEADLESS = os.path.join(HERE, "vxrt_headless")
+
+
+def build_host(force=False):
+    """the C++ host mirror of render.hpp + the headless game-loop driver, linked against libvxrt.so"""
+    if not force and os.path.exists(HEADLESS) and all(os.path.getmtime(d) <= os.path.getmtime(HEADLESS) for d in HOST_DEPS + [LIB]):
+        return HEADLESS
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", HEADLESS] + HOST_SRCS + ["-L" + HERE, "-lvxrt", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building vxrt_headless")
+    return HEADLESS
+
+
 def lib_path():
     return LIB
 
@@ -45,3 +62,4 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

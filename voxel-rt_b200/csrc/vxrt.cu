@@ -180,6 +180,13 @@ extern "C" int vxrt_device_available(void) {
 
 extern "C" const char* vxrt_last_error(void) { return g_last_error.c_str(); }
 
+extern "C" void* vxrt_host_alloc(size_t nbytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, nbytes) != cudaSuccess) { cudaGetLastError(); g_last_error = "cudaMallocHost failed"; return nullptr; }
+    return p;
+}
+extern "C" void vxrt_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 extern "C" uint64_t vxrt_fnv1a64(const void* data, size_t nbytes) {
     const uint8_t* p = (const uint8_t*)data;
     uint64_t h = 1469598103934665603ull;
@@ -493,9 +500,19 @@ extern "C" int vxrt_render_frame_host(vxrt_ctx* c, const vxrt_frame* f, uint8_t*
     if (rc != VXRT_OK) return rc;
     rc = vxrt_render(c);
     if (rc != VXRT_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(c->h_frame, c->d_rgba8, c->out_pixels * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    memcpy(out, c->h_frame, c->out_pixels * 4);
+    // pinned destination (vxrt_host_alloc / cudaHostRegister): DMA straight into it; pageable: stage through the
+    // context's pinned buffer
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        CUDA_TRY(cudaMemcpyAsync(out, c->d_rgba8, c->out_pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(c->h_frame, c->d_rgba8, c->out_pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        memcpy(out, c->h_frame, c->out_pixels * 4);
+    }
     return VXRT_OK;
 }
 
