@@ -36,8 +36,10 @@ WORKLOADS = {                     # name -> (scene, resolution key)
     "C3ii_pitched_4k": ("C3ii_pitched", "4k"),    # second camera pose
     "C2_1080p": ("C2", "1080p"),                  # configs[1]
     "C1_720p": ("C1", "720p"),                    # configs[0] (the reference's CPU-runnable case)
+    "C4_terrain_4k": ("C4", "4k"),                # configs[3]: synthetic 1024^3 terrain (4 GiB grid per GPU), 16 lights
+    "C5_edits_4k": ("C5", "4k"),                  # configs[4]: one right-click edit (r = 7) before every frame, pitched pose
 }
-METRIC = "Mrays/sec (primary+shadow), reference default level, 16 local lights"
+METRIC = "Mrays/sec (primary+shadow)"
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -149,15 +151,30 @@ def run_b200(args):
 
     scene, reskey = WORKLOADS[args.workload]
     W, H = vx.scenes.RESOLUTIONS[reskey]
-    frame = vx.scenes.frame_for(scene, W, H)
 
     # ---- grid: every rank builds its replica; level generation + depth field are outside the timed region ----
-    ren = vx.Renderer(grid=vx.scenes.DEFAULT_GRID, width=W, height=H, device=local_rank, rank=rank, world=world)
-    ren.initVoxels()                                              # device level generator (level.cpp:82-138)
-    ren.buildDepthField()                                         # device depth-field builder (render.cpp:273-286)
-    level_arr = ren.downloadGrid()
-    level_fnv = "%016x" % vx.scenes.fnv1a64(level_arr)
-    assert level_fnv == "4c58cc4001a22afa", level_fnv            # the reference level, bit for bit
+    build_info = {}
+    if scene == "C4":
+        grid = vx.scenes.TERRAIN_GRID
+        ren = vx.Renderer(grid=grid, width=W, height=H, device=local_rank, rank=rank, world=world)
+        t0 = time.perf_counter(); ren.generateTerrain(vx.scenes.TERRAIN_SEED); t1 = time.perf_counter()
+        ren.buildDepthField(); t2 = time.perf_counter()
+        build_info = {"terrain_generate_s": round(t1 - t0, 3), "depth_field_build_s": round(t2 - t1, 3)}
+        frame = vx.scenes.terrain_frame(W, H, ren.terrainHeight(grid[0] // 2, grid[2] // 2))
+        level_arr = None
+        level_fnv = "terrain seed 0x5EED (integer fbm, include/vxrt.h)"
+    else:
+        grid = vx.scenes.DEFAULT_GRID
+        frame = vx.scenes.frame_for("C3ii_pitched" if scene == "C5" else scene, W, H)
+        ren = vx.Renderer(grid=grid, width=W, height=H, device=local_rank, rank=rank, world=world)
+        t0 = time.perf_counter(); ren.initVoxels(); t1 = time.perf_counter()      # device level generator (level.cpp:82-138)
+        ren.buildDepthField(); t2 = time.perf_counter()                           # device depth-field builder (render.cpp:273-286)
+        build_info = {"level_generate_s": round(t1 - t0, 3), "depth_field_build_s": round(t2 - t1, 3)}
+        level_arr = ren.downloadGrid()
+        level_fnv = "%016x" % vx.scenes.fnv1a64(level_arr)
+        assert level_fnv == "4c58cc4001a22afa", level_fnv        # the reference level, bit for bit
+    edits = vx.scenes.edit_centres(1000) if scene == "C5" else None
+    edit_state = {"k": 0}
 
     stream = torch.cuda.ExternalStream(ren.stream_ptr(), device=torch.device("cuda", local_rank))
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
@@ -173,11 +190,25 @@ def run_b200(args):
 
     def step_device():
         """one frame with inputs resident: kernels (+ gather + un-tile for N > 1) on the renderer's stream"""
+        apply_edit()
         ren.draw()
         if world > 1:
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(gathered, local_t)
             ren.assembleTiles(gathered.data_ptr(), final.data_ptr())
+
+    def apply_edit():
+        if edits is not None:                                     # C5: right-click destruction before every frame
+            k = edit_state["k"] % len(edits)
+            edit_state["k"] += 1
+            if world > 1:                                         # rank 0 decides, the 16-byte command is broadcast (NCCL)
+                cmd = torch.tensor([int(edits[k][0]), int(edits[k][1]), int(edits[k][2]), 7] if rank == 0 else [0, 0, 0, 0],
+                                   dtype=torch.int32, device="cuda")
+                dist.broadcast(cmd, src=0)
+                c = cmd.tolist()
+            else:
+                c = [int(edits[k][0]), int(edits[k][1]), int(edits[k][2]), 7]
+            ren.removeSphere(c[:3], c[3])
 
     def flush_l2():
         with torch.cuda.stream(stream):
@@ -191,11 +222,11 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)                            # samples through warm-up, timed region and e2e loop
     sampler.start()
     ren.updateUniforms(frame)
-    t_warm = time.perf_counter()
-    nwarm = 0
-    while nwarm < max(args.warmup, 3) or time.perf_counter() - t_warm < 0.5:     # >= 0.5 s so that clocks settle
-        flush_l2(); step_device(); nwarm += 1
-        if nwarm % 16 == 0:
+    # W warm-up frames as asked, plus a fixed 200 more (same count on every rank: the frames contain collectives)
+    # so that clocks settle and the nvidia-smi sampler sees the GPU under load
+    for nwarm in range(max(args.warmup, 3) + 200):
+        flush_l2(); step_device()
+        if nwarm % 16 == 15:
             ren.sync()
     barrier()
     st = ren.stats()
@@ -240,7 +271,8 @@ def run_b200(args):
 
     def step_e2e():
         if world == 1:
-            ren.renderFrameHost(frame, host_out)                  # set_frame + kernels + D2H (pinned staging) + sync
+            apply_edit()
+            ren.renderFrameHost(frame, host_out)                  # set_frame + kernels + D2H into page-locked memory + sync
         else:
             ren.updateUniforms(frame)
             step_device()
@@ -289,7 +321,8 @@ def run_b200(args):
             "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (reference procedural default level, fnv1a64 %s; fixed camera)" % level_fnv,
-            "config": {"workload": args.workload, "grid": list(vx.scenes.DEFAULT_GRID), "width": W, "height": H, "local_lights": 16 if scene != "C1" else 0,
+            "config": {"workload": args.workload, "grid": list(grid), "width": W, "height": H, "local_lights": 16 if scene != "C1" else 0,
+                       "setup": build_info,
                        "view_depth_field": int(frame.view_depth_field), "rays_per_frame": rays, "rays_primary": rp, "rays_global": rg,
                        "rays_local": rl, "voxel_fetches_per_frame": fetches, "hit_pixels": hits,
                        "partition": "sort-first 32x8 tiles, tile t -> rank t %% %d, grid replicated, NCCL all-gather of RGBA8 tiles" % world,
@@ -302,13 +335,21 @@ def run_b200(args):
             "roofline": roofline,
             "wall_s_timed_region": round(t_wall, 3),
         }
-        if not args.no_extra and world == 1:
+        if scene == "C5":
+            result["config"]["edits"] = "one vxrt_edit_remove_sphere(r=7) per frame, centres from mt19937(12345); rays/fetches are those of the last frame"
+        if not args.no_extra and world == 1 and scene not in ("C4", "C5"):
             result["other_workloads"] = extra_workloads(vx, ren, flush_l2, stream, torch)
             result["cpu_baseline"] = cpu_baseline(args.workload, level=level_arr)
-    ren.close()
+    # teardown order matters: torch tensors that were used on the renderer's stream must be released (their
+    # allocator records events on that stream) BEFORE the renderer destroys it
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+        del gathered, final, local_t
+    del flush, final_host
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    ren.close()
     if rank == 0:
         print(json.dumps(result))
 

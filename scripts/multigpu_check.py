@@ -74,9 +74,12 @@ def main():
         print("frame after broadcast edits vs oracle:", np.array_equal(got_edit, want2))
         ok &= all(f == o.fnv(level) for f in fnvs)
         print("replica fingerprints equal oracle:", all(f == o.fnv(level) for f in fnvs), ["%016x" % f for f in fnvs])
-    ren.close()
     dist.barrier()
     dist.destroy_process_group()
+    del gathered, final, local_t
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    ren.close()
     if rank == 0:
         print("MULTIGPU CHECK", "PASS" if ok else "FAIL")
         sys.exit(0 if ok else 1)

@@ -48,6 +48,20 @@ def frame_for(name, width, height, grid=DEFAULT_GRID):
     raise KeyError(name)
 
 
+TERRAIN_GRID = (1024, 1024, 1024)                # config C4: 4 GiB of int32 voxels, replicated per GPU
+TERRAIN_SEED = 0x5EED
+
+
+def terrain_frame(width, height, surface_at_cam, grid=TERRAIN_GRID, view=0):
+    """config C4: camera above the middle of the synthetic terrain, pitched pose, sun at
+    (w/2, 3w, w/2), 16 lights on the 4x4 pattern 4 voxels above the surface height under the camera."""
+    aspect = np.float32(width) / np.float32(height)
+    cam = (grid[0] / 2.0, float(surface_at_cam + 20), grid[2] / 2.0)
+    light = (grid[0] / 2.0, grid[0] * 3.0, grid[2] / 2.0)
+    return make_frame(cam, rotate=PITCHED_ROTATE, light_pos=light, aspect=aspect, view=view,
+                      lights=lights_4x4(cam, y=float(surface_at_cam + 4)), cam_rotation=(0.5, 0.6))
+
+
 def edit_centres(n, seed=12345):
     """C5: n destruction centres from the MT19937 stream seeded like std::mt19937(seed) (numpy's legacy
     RandomState uses the same init_genrand): x,z in [20,491], y in [30,44]."""
