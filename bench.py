@@ -229,7 +229,11 @@ def run_b200(args):
         if nwarm % 16 == 15:
             ren.sync()
     barrier()
-    st = ren.stats()
+    st = ren.stats()                                              # ray / fetch counts of this frame (counters on)
+    ren.setStats(False)                                           # production frames: no per-iteration counters
+    for nwarm in range(3):
+        flush_l2(); step_device()
+    barrier()
     # ---- timed region: K frames, each bracketed by CUDA events on the launching stream, L2 flushed in between ----
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kern_ms = {"primary": [], "shade": []}
@@ -362,6 +366,7 @@ def extra_workloads(vx, ren, flush_l2, stream, torch, steps=10):
         W, H = vx.scenes.RESOLUTIONS[reskey]
         ren.reshape(W, H)
         ren.updateUniforms(vx.scenes.frame_for(scene, W, H))
+        ren.setStats(False)
         for _ in range(3):
             flush_l2(); ren.draw()
         ren.sync()
@@ -371,7 +376,7 @@ def extra_workloads(vx, ren, flush_l2, stream, torch, steps=10):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream); ren.draw(); b.record(stream); ren.sync()
             ms.append(a.elapsed_time(b))
-        st = ren.stats()
+        ren.setStats(True); ren.draw(); st = ren.stats(); ren.setStats(False)
         rays = vx.scenes.total_rays(st)
         m = statistics.mean(ms)
         out[name] = {"ms_per_frame": round(m, 4), "Mrays_per_s": round(rays / (m * 1e-3) / 1e6, 2), "rays_per_frame": rays,

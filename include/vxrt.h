@@ -135,6 +135,10 @@ int vxrt_resize(vxrt_ctx* ctx, int width, int height);
 /* glDrawArrays(GL_TRIANGLES,0,6) main.cpp:59: runs the per-pixel path for this context's tiles; asynchronous */
 int vxrt_render(vxrt_ctx* ctx);
 int vxrt_sync(vxrt_ctx* ctx);
+/* enabled (default): every vxrt_render maintains the fetch / local-ray counters of vxrt_stats.  Disabled: the
+   kernels skip the per-iteration counter (rays_local / fetches read back as 0; hit_pixels, rays_primary,
+   rays_global and the timings stay valid).  Same pixels either way. */
+int vxrt_set_stats(vxrt_ctx* ctx, int enabled);
 /* set_frame + render + device->host copy of the RGBA8 frame into out (width*height*4 bytes) + sync.
    world > 1: out receives this rank's tiles in gather layout (vxrt_local_bytes()). */
 int vxrt_render_frame_host(vxrt_ctx* ctx, const vxrt_frame* frame, uint8_t* out);

@@ -115,6 +115,35 @@ def test_camera_inside_solid_and_outside_grid(vx, oracle, default_level, ren):
         check_frame(vx, oracle, ren, default_level, gc.DIMS, fr, W, H)
 
 
+def test_production_variant_without_counters_renders_the_same_pixels(vx, default_level):
+    """vxrt_set_stats(0) selects the kernel variants without the per-iteration counter; frames must not change"""
+    W, H = 320, 180
+    for dims_level in ("ref", "other"):
+        if dims_level == "ref":
+            dims, level = gc.DIMS, default_level
+        else:
+            dims = (64, 48, 80)
+            level = np.full(dims[0] * dims[1] * dims[2], -1, np.int32)
+            level.reshape(dims[2], dims[1], dims[0])[:, :20, :] = 0x804020
+        with vx.Renderer(grid=dims, width=W, height=H) as r:
+            r.updateGeometry(level)
+            if dims_level == "other":
+                r.buildDepthField()
+            for name in ("C2", "C3i", "C3ii_pitched"):
+                fr = to_vx_frame(vx, gc.frame_cases(W, H)[name])
+                if dims_level == "other":
+                    fr.cam_pos[:] = [30.0, 30.0, 10.0]
+                r.setStats(True)
+                a = r.renderFrameHost(fr)
+                sa = r.stats()
+                r.setStats(False)
+                b = r.renderFrameHost(fr)
+                sb = r.stats()
+                assert np.array_equal(a, b), (dims_level, name)
+                assert sa["hit_pixels"] == sb["hit_pixels"] and sa["rays_global"] == sb["rays_global"]
+                assert sa["fetches"] > 0 and (sb["fetches"] == 0 or name == "C3i")
+
+
 def test_render_is_idempotent_and_view_toggle(vx, ren):
     W, H = 160, 90
     ren.reshape(W, H)

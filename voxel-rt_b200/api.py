@@ -72,6 +72,7 @@ _SIGNATURES = {
     "vxrt_resize": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "vxrt_render": (C.c_int, [C.c_void_p]),
     "vxrt_sync": (C.c_int, [C.c_void_p]),
+    "vxrt_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_render_frame_host": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p]),
     "vxrt_read_rgba8": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vxrt_read_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -269,6 +270,10 @@ class Renderer:
     def draw(self):
         """glDrawArrays(GL_TRIANGLES,0,6) main.cpp:59 (asynchronous)."""
         self._check(self.lib.vxrt_render(self._h))
+
+    def setStats(self, enabled):
+        """fetch / local-ray counters on (default) or off (production frames: one issue slot less per DDA iteration)"""
+        self._check(self.lib.vxrt_set_stats(self._h, 1 if enabled else 0))
 
     def sync(self):
         self._check(self.lib.vxrt_sync(self._h))

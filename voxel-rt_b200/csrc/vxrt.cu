@@ -57,6 +57,7 @@ struct vxrt_ctx {
     uint8_t* h_frame = nullptr;         // pinned read-back buffer
     size_t h_frame_cap = 0;
     bool rendered = false;
+    bool count_stats = true;            // vxrt_set_stats: maintain fetch / local-ray counters (costs ~1 issue slot per DDA iteration)
     uint32_t launches = 0;
 };
 
@@ -474,17 +475,42 @@ extern "C" int vxrt_render(vxrt_ctx* c) {                                       
     c->launches = 0;
     CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    primary_kernel<<<c->map.nlocal, 256, 0, c->stream>>>(g, fp, c->map, o);
+    // kernel variants: iteration counting on/off (the step-count view and the debug planes always need it), and the
+    // reference's compile-time grid extents (512 x 96 x 512) vs runtime extents
+    const bool count = c->count_stats || c->d_dbg_hit != nullptr;
+    const bool count_primary = count || c->frame.view_depth_field == 1;
+    const bool ref_dims = (g.w == GridViewRef::w && g.h == GridViewRef::h && g.d == GridViewRef::d);
+    GridViewRef gr; gr.vox = g.vox;
+    const dim3 grid(c->map.nlocal), block(256);
+    if (ref_dims) {
+        if (count_primary) primary_kernel<true, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, c->map, o);
+        else primary_kernel<false, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, c->map, o);
+    } else {
+        if (count_primary) primary_kernel<true, GridView><<<grid, block, 0, c->stream>>>(g, fp, c->map, o);
+        else primary_kernel<false, GridView><<<grid, block, 0, c->stream>>>(g, fp, c->map, o);
+    }
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     if (c->frame.view_depth_field != 1) {
-        shade_kernel<<<c->map.nlocal, 256, 0, c->stream>>>(g, fp, c->map, o);
+        if (ref_dims) {
+            if (count) shade_kernel<true, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, c->map, o);
+            else shade_kernel<false, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, c->map, o);
+        } else {
+            if (count) shade_kernel<true, GridView><<<grid, block, 0, c->stream>>>(g, fp, c->map, o);
+            else shade_kernel<false, GridView><<<grid, block, 0, c->stream>>>(g, fp, c->map, o);
+        }
         CUDA_TRY(cudaGetLastError());
         c->launches++;
     }
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
     c->rendered = true;
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_set_stats(vxrt_ctx* c, int enabled) {
+    if (!c) return fail(VXRT_ERR_INVALID, "null context");
+    c->count_stats = enabled != 0;
     return VXRT_OK;
 }
 
