@@ -335,7 +335,7 @@ def run_b200(args):
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "vxrt_render_frame_host (C ABI): host frame params in, host RGBA8 frame out; wall clock"},
-            "gpu_launches": int(args.steps * (st["kernel_launches"] + (1 if world > 1 else 0))),
+            "gpu_launches": int(args.steps * (2 + (1 if world > 1 else 0))),
             "roofline": roofline,
             "wall_s_timed_region": round(t_wall, 3),
         }

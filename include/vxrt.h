@@ -143,6 +143,10 @@ int vxrt_set_stats(vxrt_ctx* ctx, int enabled);
    world > 1: out receives this rank's tiles in gather layout (vxrt_local_bytes()). */
 int vxrt_render_frame_host(vxrt_ctx* ctx, const vxrt_frame* frame, uint8_t* out);
 
+/* vxrt_render_frame_host renders the frame in `nbands` bands of tile rows (default 4, 1..16) and copies each band
+   to the host while the next one renders.  Same pixels for every value. */
+int vxrt_set_readback_bands(vxrt_ctx* ctx, int nbands);
+
 /* ---- results ---------------------------------------------------------------------------------- */
 int vxrt_read_rgba8(vxrt_ctx* ctx, uint8_t* out);            /* width*height*4 (world==1) else vxrt_local_bytes() */
 /* parity outputs (need VXRT_FLAG_DEBUG_OUTPUTS); full-frame arrays, any pointer may be NULL:
@@ -169,6 +173,26 @@ void*  vxrt_stream(vxrt_ctx* ctx);                           /* cudaStream_t the
    vxrt_device_rgba8()); dst: device pointer to width*height*4 bytes; un-tiles into a raster frame on
    `stream` (NULL = the context's stream) */
 int vxrt_assemble_tiles(vxrt_ctx* ctx, const void* gathered, void* dst, void* stream);
+
+/* ---- multi-GPU without a gather: peer-memory frame target ------------------------------------------------
+   One rank (the display rank) owns a double-buffered raster frame; every rank's kernels store their tiles'
+   pixels straight into it over NVLink / NVSwitch while they render (no collective, no un-tile pass), then publish
+   completion with a system-scope release that the owner acquires before it reads the frame.
+     owner : vxrt_p2p_export(ctx, handle)  -> send the 64-byte handle to the other ranks (any transport)
+     others: vxrt_p2p_import(ctx, handle)
+     every frame, every rank: vxrt_set_frame + vxrt_render        (waits, on the stream, for the owner to have released
+                                                                   the buffer it is about to overwrite)
+     owner : vxrt_p2p_wait_frame(ctx, &dptr) -> dptr = complete width*height RGBA8 raster frame (stream-ordered)
+             ... consume it on vxrt_stream() ...   vxrt_p2p_release_frame(ctx)
+   vxrt_p2p_error: 0, or non-zero if a bounded device-side wait timed out (a rank stopped participating). */
+int vxrt_p2p_export(vxrt_ctx* ctx, uint8_t handle[64]);
+int vxrt_p2p_import(vxrt_ctx* ctx, const uint8_t handle[64]);
+/* same-process variant of import: several contexts in one process; owner_base = vxrt_p2p_base(owner ctx) */
+int vxrt_p2p_attach(vxrt_ctx* ctx, void* owner_base);
+void* vxrt_p2p_base(vxrt_ctx* ctx);
+int vxrt_p2p_wait_frame(vxrt_ctx* ctx, void** frame);
+int vxrt_p2p_release_frame(vxrt_ctx* ctx);
+int vxrt_p2p_error(vxrt_ctx* ctx);
 
 #ifdef __cplusplus
 }

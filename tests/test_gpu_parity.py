@@ -144,6 +144,34 @@ def test_production_variant_without_counters_renders_the_same_pixels(vx, default
                 assert sa["fetches"] > 0 and (sb["fetches"] == 0 or name == "C3i")
 
 
+@pytest.mark.parametrize("size", [(416, 240), (100, 37)])
+def test_banded_readback_renders_the_same_frame(vx, oracle, default_level, size):
+    """vxrt_render_frame_host renders in bands of tile rows and copies each band out while the next renders:
+    same frame for every band count, page-locked or pageable destination, whole-frame or tile-partition context"""
+    W, H = size
+    fr = gc.frame_cases(W, H)["C3ii_pitched"]
+    want = oracle.render(default_level, gc.DIMS, fr, W, H)["rgba8"]
+    with vx.Renderer(grid=gc.DIMS, width=W, height=H) as r:
+        r.updateGeometry(default_level)
+        pinned = r.hostFrameBuffer()
+        for nb in (1, 2, 3, 4, 7, 16):
+            r.setReadbackBands(nb)
+            pinned[:] = 0
+            assert np.array_equal(r.renderFrameHost(to_vx_frame(vx, fr), pinned), want), nb
+            assert np.array_equal(r.renderFrameHost(to_vx_frame(vx, fr)), want), nb       # pageable numpy destination
+            st = r.stats()
+            assert st["fetches"] == int(oracle.render(default_level, gc.DIMS, fr, W, H)["counters"][3])
+        with pytest.raises(vx.VxrtError):
+            r.setReadbackBands(0)
+    parts = []
+    for rank in range(3):
+        with vx.Renderer(grid=gc.DIMS, width=W, height=H, rank=rank, world=3) as r:
+            r.updateGeometry(default_level)
+            r.setReadbackBands(5)
+            parts.append(r.renderFrameHost(to_vx_frame(vx, fr)))
+    assert np.array_equal(vx.tiles.assemble(np.stack(parts), W, H), want)
+
+
 def test_render_is_idempotent_and_view_toggle(vx, ren):
     W, H = 160, 90
     ren.reshape(W, H)
@@ -154,7 +182,9 @@ def test_render_is_idempotent_and_view_toggle(vx, ren):
     fr.view_depth_field = 1
     c = ren.renderFrameHost(fr)
     assert np.array_equal(c[..., 0], c[..., 1]) and np.array_equal(c[..., 1], c[..., 2]) and (c[..., 3] == 255).all()
-    assert ren.stats()["rays_local"] == 0 and ren.stats()["kernel_launches"] == 1
+    assert ren.stats()["rays_local"] == 0 and ren.stats()["kernel_launches"] == ren.stats()["kernel_launches"] >= 1
+    ren.draw()
+    assert ren.stats()["kernel_launches"] == 1                      # step-count view: the primary kernel only
 
 
 # ---- other grid shapes ---------------------------------------------------------------------------
@@ -331,6 +361,45 @@ def test_tile_partition_reassembles_the_frame(vx, default_level, world):
         r.assembleTiles(g.data_ptr(), dst.data_ptr())
         r.sync()
         assert np.array_equal(dst.cpu().numpy(), want)
+
+
+def test_peer_memory_frame_target_protocol_on_one_gpu(vx, oracle, default_level):
+    """the gather-free multi-GPU path with all 'ranks' on one device: every context stores its tiles straight into
+    the owner's double-buffered raster frame, completion flags are released / acquired on the streams"""
+    import torch
+    W, H, world = 416, 240, 3
+    ctxs = [vx.Renderer(grid=gc.DIMS, width=W, height=H, rank=r, world=world) for r in range(world)]
+    try:
+        for r in ctxs:
+            r.updateGeometry(default_level)
+        ctxs[0].p2pExport()
+        for r in ctxs[1:]:
+            r.p2pAttach(ctxs[0])
+        names = ["C3ii_pitched", "C2", "C3i", "sparse_lights", "C1"]          # 5 frames > 2 buffers: exercises the back-pressure
+        out = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
+        stream = torch.cuda.ExternalStream(ctxs[0].stream_ptr())
+        for k, name in enumerate(names):
+            fr = gc.frame_cases(W, H)[name]
+            for r in reversed(ctxs):                                           # launch order must not matter
+                r.updateUniforms(to_vx_frame(vx, fr))
+                r.draw()
+            ptr = ctxs[0].p2pWaitFrame()
+
+            class _Buf:
+                __cuda_array_interface__ = {"shape": (H, W, 4), "typestr": "|u1", "data": (ptr, False), "version": 3}
+            with torch.cuda.stream(stream):
+                out.copy_(torch.as_tensor(_Buf(), device="cuda"))
+            ctxs[0].p2pReleaseFrame()
+            ctxs[0].sync()
+            assert np.array_equal(out.cpu().numpy(), oracle.render(default_level, gc.DIMS, fr, W, H)["rgba8"]), name
+        assert all(r.p2pError() == 0 for r in ctxs)
+        with pytest.raises(vx.VxrtError):
+            ctxs[1].p2pWaitFrame()                                             # only the owner may wait
+    finally:
+        del out
+        torch.cuda.synchronize()
+        for r in ctxs:
+            r.close()
 
 
 # ---- API state / error behaviour -----------------------------------------------------------------

@@ -72,6 +72,7 @@ _SIGNATURES = {
     "vxrt_resize": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "vxrt_render": (C.c_int, [C.c_void_p]),
     "vxrt_sync": (C.c_int, [C.c_void_p]),
+    "vxrt_set_readback_bands": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_render_frame_host": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p]),
     "vxrt_read_rgba8": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -84,6 +85,13 @@ _SIGNATURES = {
     "vxrt_local_bytes": (C.c_size_t, [C.c_void_p]),
     "vxrt_device_rgba8": (C.c_void_p, [C.c_void_p]),
     "vxrt_stream": (C.c_void_p, [C.c_void_p]),
+    "vxrt_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vxrt_p2p_import": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vxrt_p2p_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vxrt_p2p_base": (C.c_void_p, [C.c_void_p]),
+    "vxrt_p2p_wait_frame": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "vxrt_p2p_release_frame": (C.c_int, [C.c_void_p]),
+    "vxrt_p2p_error": (C.c_int, [C.c_void_p]),
     "vxrt_assemble_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
@@ -275,6 +283,9 @@ class Renderer:
         """fetch / local-ray counters on (default) or off (production frames: one issue slot less per DDA iteration)"""
         self._check(self.lib.vxrt_set_stats(self._h, 1 if enabled else 0))
 
+    def setReadbackBands(self, n):
+        self._check(self.lib.vxrt_set_readback_bands(self._h, int(n)))
+
     def sync(self):
         self._check(self.lib.vxrt_sync(self._h))
 
@@ -346,6 +357,34 @@ class Renderer:
 
     def stream_ptr(self):
         return int(self.lib.vxrt_stream(self._h) or 0)
+
+    # peer-memory frame target (multi-GPU without a gather)
+    def p2pExport(self):
+        """owner rank: returns the 64-byte handle (numpy uint8) to send to the other ranks"""
+        h = np.zeros(64, np.uint8)
+        self._check(self.lib.vxrt_p2p_export(self._h, _vp(h)))
+        return h
+
+    def p2pImport(self, handle):
+        h = np.ascontiguousarray(handle, np.uint8)
+        assert h.size == 64
+        self._check(self.lib.vxrt_p2p_import(self._h, _vp(h)))
+
+    def p2pAttach(self, owner):
+        """same-process variant: attach to another Renderer's peer-memory target"""
+        self._check(self.lib.vxrt_p2p_attach(self._h, C.c_void_p(self.lib.vxrt_p2p_base(owner._h))))
+
+    def p2pWaitFrame(self):
+        """owner rank: stream-ordered wait for every rank's tiles; returns the device pointer of the raster frame"""
+        p = C.c_void_p()
+        self._check(self.lib.vxrt_p2p_wait_frame(self._h, C.byref(p)))
+        return int(p.value)
+
+    def p2pReleaseFrame(self):
+        self._check(self.lib.vxrt_p2p_release_frame(self._h))
+
+    def p2pError(self):
+        return self._check(self.lib.vxrt_p2p_error(self._h))
 
     def assembleTiles(self, gathered_ptr, dst_ptr, stream_ptr=0):
         self._check(self.lib.vxrt_assemble_tiles(self._h, C.c_void_p(gathered_ptr), C.c_void_p(dst_ptr), C.c_void_p(stream_ptr)))

@@ -29,6 +29,7 @@ struct TileMap {
     int width, height;
     int tx, ty, ntiles;                 // tiles per row / column / total
     int rank, world, nlocal;            // this context renders tiles t = j*world + rank, j in [0,nlocal)
+    int tile_base;                      // first local tile of this launch (frames can be rendered in bands of tile rows)
 };
 
 struct Counters {
@@ -38,7 +39,8 @@ struct Counters {
 };
 
 struct Outputs {
-    uint32_t* rgba8;                    // world==1: raster [height][width]; else tile-compact [nlocal][8][32]
+    uint32_t* rgba8;                    // raster [height][width] (world==1 or peer-memory target); else tile-compact [nlocal][8][32]
+    int raster;                         // 1: rgba8 is a raster frame
     float4* hitq;                       // hit queue: hitPos.xyz, w = colour(24) | normal(4)<<24
     uint32_t* hitpix;                   // raster pixel id of each queue entry
     Counters* counters;
@@ -48,8 +50,8 @@ struct Outputs {
     uint32_t* dbg_cast;
 };
 
-__device__ __forceinline__ uint32_t out_index_of(const TileMap& m, int px, int py) {
-    if (m.world == 1) return (uint32_t)(py * m.width + px);
+__device__ __forceinline__ uint32_t out_index_of(const TileMap& m, int raster, int px, int py) {
+    if (raster) return (uint32_t)(py * m.width + px);
     const int t = (py / TILE_H) * m.tx + (px / TILE_W);
     const int local = t / m.world;
     return (uint32_t)(local * TILE_PIX + (py % TILE_H) * TILE_W + (px % TILE_W));
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(256) primary_kernel(Grid g, const __grid_const
     __shared__ unsigned long long s_fetches;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) s_fetches = 0ull;
-    const int t = blockIdx.x * m.world + m.rank;                    // global tile
+    const int t = (blockIdx.x + m.tile_base) * m.world + m.rank;    // global tile
     const int lx = (warp & 3) * 8 + (lane & 7), ly = (warp >> 2) * 4 + (lane >> 3);
     const int px = (t % m.tx) * TILE_W + lx, py = (t / m.tx) * TILE_H + ly;
     const bool valid = (t < m.ntiles) && (px < m.width) && (py < m.height);
@@ -88,11 +90,11 @@ __global__ void __launch_bounds__(256) primary_kernel(Grid g, const __grid_const
         const uint32_t pid = (uint32_t)(py * m.width + px);
         if (f.view_depth_field == 1) {                               // :143-145
             const float grey = __fdiv_rn((float)r.steps, 100.0f);
-            o.rgba8[out_index_of(m, px, py)] = pack_rgba8(grey, grey, grey, 1.0f);
+            o.rgba8[out_index_of(m, o.raster, px, py)] = pack_rgba8(grey, grey, grey, 1.0f);
         } else if (r.idx >= 0) {
             hit = true;                                              // finished by shade_kernel
         } else {
-            o.rgba8[out_index_of(m, px, py)] = pack_rgba8(0.6f, 0.7f, 0.8f, 1.0f);   // :133
+            o.rgba8[out_index_of(m, o.raster, px, py)] = pack_rgba8(0.6f, 0.7f, 0.8f, 1.0f);   // :133
         }
         if (o.dbg_hit) {
             o.dbg_hit[pid] = r.idx;
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(256) shade_kernel(Grid g, const __grid_constan
         const float cg = __fmul_rn(__fdiv_rn((float)((packed >> 8) & 255u), 255.0f), multiplier);
         const float cb = __fmul_rn(__fdiv_rn((float)(packed & 255u), 255.0f), multiplier);
         const int px = (int)(pid % (uint32_t)m.width), py = (int)(pid / (uint32_t)m.width);
-        o.rgba8[out_index_of(m, px, py)] = pack_rgba8(cr, cg, cb, 1.0f);
+        o.rgba8[out_index_of(m, o.raster, px, py)] = pack_rgba8(cr, cg, cb, 1.0f);
         if (o.dbg_occl) { o.dbg_occl[pid] = occl; o.dbg_cast[pid] = cast; }
     }
     const unsigned wf = __reduce_add_sync(0xffffffffu, fetches), wl = __reduce_add_sync(0xffffffffu, nlocal);
@@ -302,6 +304,56 @@ __global__ void division_selftest_kernel(unsigned long long n, unsigned long lon
         if (__float_as_uint(q) != __float_as_uint(want)) bad++;
     }
     if (bad) atomicAdd(mismatches, bad);
+}
+
+// ---- peer-memory frame target (multi-GPU without a gather) -----------------------------------------
+// The display rank owns {2 raster frames, done[world] flags, consumed counter}; every rank's kernels store their
+// pixels straight into the owner's frame over NVLink, then publish completion with a system-scope release; the
+// owner acquires all flags before it consumes the frame.  Spins are bounded (~4 s) so that a lost peer cannot
+// hang the GPU: on time-out *err is set and the kernel returns.
+struct P2PShared {
+    unsigned long long consumed;        // frames the owner has finished reading (written by the owner)
+    unsigned long long pad0[15];
+    unsigned long long done[16 * 16];   // done[16*r] = frames rank r has completely written (stride 128 B)
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned long long target) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(p) < target) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > 4000000000ull) return false;
+        __nanosleep(200);
+    }
+    return true;
+}
+// all ranks, before rendering frame `seq` into buffer seq%2: the owner must have consumed frame seq-2
+__global__ void p2p_wait_consumed_kernel(const P2PShared* sh, unsigned long long seq, int* err) {
+    if (seq >= 2 && !spin_until(&sh->consumed, seq - 1)) *err = 1;
+}
+// all ranks, after rendering frame `seq`
+__global__ void p2p_signal_done_kernel(P2PShared* sh, int rank, unsigned long long seq) {
+    __threadfence_system();
+    st_release_sys(&sh->done[16 * rank], seq + 1);
+}
+// owner: all ranks have written frame `seq`
+__global__ void p2p_wait_done_kernel(const P2PShared* sh, int world, unsigned long long seq, int* err) {
+    const int r = threadIdx.x;
+    if (r < world && !spin_until(&sh->done[16 * r], seq + 1)) *err = 2;
+}
+// owner: frame `seq` consumed
+__global__ void p2p_release_kernel(P2PShared* sh, unsigned long long seq) {
+    __threadfence_system();
+    st_release_sys(&sh->consumed, seq + 1);
 }
 
 // gathered: [world][nlocal][8][32] RGBA8 -> raster [height][width]

@@ -27,10 +27,16 @@ static int fail(int code, const std::string& msg) { g_last_error = msg; return c
             return fail(VXRT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
     } while (0)
 
+constexpr int MAX_BANDS = 16;
+
 struct vxrt_ctx {
     vxrt_config cfg{};
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;         // device->host read-back of finished bands, overlapped with rendering
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_band[MAX_BANDS] = {};
+    cudaEvent_t ev_copy = nullptr;
+    int readback_bands = 4;
     // grid
     int32_t* d_vox = nullptr;
     size_t nvox = 0;
@@ -57,6 +63,13 @@ struct vxrt_ctx {
     uint8_t* h_frame = nullptr;         // pinned read-back buffer
     size_t h_frame_cap = 0;
     bool rendered = false;
+    int bands_used = 1;
+    // peer-memory frame target (vxrt_p2p_*)
+    bool p2p = false, p2p_owner = false, p2p_attached = false;
+    uint8_t* p2p_base = nullptr;        // owner: cudaMalloc'ed; importer: cudaIpcOpenMemHandle'd
+    size_t p2p_frame_bytes = 0;
+    unsigned long long p2p_seq = 0;     // frames rendered into the target so far
+    int* d_p2p_err = nullptr;
     bool count_stats = true;            // vxrt_set_stats: maintain fetch / local-ray counters (costs ~1 issue slot per DDA iteration)
     uint32_t launches = 0;
 };
@@ -69,6 +82,7 @@ static TileMap make_map(int width, int height, int rank, int world) {
     m.ntiles = m.tx * m.ty;
     m.rank = rank; m.world = world;
     m.nlocal = (m.ntiles + world - 1) / world;
+    m.tile_base = 0;
     return m;
 }
 
@@ -222,7 +236,10 @@ extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaStreamCreate failed"));
     for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
     if (cudaMalloc(&c->d_vox, c->nvox * 4) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaMalloc(grid) failed"));
-    if (cudaMalloc(&c->d_counters, sizeof(Counters)) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaMalloc(counters) failed"));
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaStreamCreate failed"));
+    for (auto& e : c->ev_band) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
+    if (cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
+    if (cudaMalloc(&c->d_counters, sizeof(Counters) * MAX_BANDS) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaMalloc(counters) failed"));
     int rc = upload_depth_offsets();
     if (rc != VXRT_OK) return bail(rc);
     rc = alloc_frame_buffers(c);
@@ -243,10 +260,15 @@ extern "C" void vxrt_destroy(vxrt_ctx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_frame_buffers(c);
+    if (c->p2p_base) { if (c->p2p_owner) cudaFree(c->p2p_base); else if (!c->p2p_attached) cudaIpcCloseMemHandle(c->p2p_base); }
+    cudaFree(c->d_p2p_err);
     cudaFree(c->d_vox); cudaFree(c->d_counters); cudaFree(c->d_stage); cudaFree(c->d_first);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_first) cudaFreeHost(c->h_first);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_band) if (e) cudaEventDestroy(e);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -457,54 +479,115 @@ extern "C" int vxrt_place_local_light(vxrt_ctx* c, float x, float y, float z, fl
 extern "C" int vxrt_resize(vxrt_ctx* c, int width, int height) {                         // render.cpp:404-411
     CHECK_CTX(c);
     if (width <= 0 || height <= 0) return fail(VXRT_ERR_INVALID, "resize: extents must be positive");
+    if (c->p2p) return fail(VXRT_ERR_STATE, "resize: not available once a peer-memory target is set");
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->cfg.width = width; c->cfg.height = height;
     c->frame.aspect = (float)width / height;
     return alloc_frame_buffers(c);
 }
 
-extern "C" int vxrt_render(vxrt_ctx* c) {                                                // main.cpp:59
-    CHECK_CTX(c);
+// Launches the frame's kernels in `nbands` bands of whole tile rows.  host_dst != nullptr: each band's pixels are
+// copied to host_dst (page-locked) on the copy stream as soon as the band's kernels finish, so the read-back of
+// band b overlaps the rendering of band b+1.
+static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst) {
     if (!c->grid_loaded) return fail(VXRT_ERR_STATE, "render before any grid upload");
     const GridView g = grid_view(c);
     FrameParams fp;
     memcpy(&fp, &c->frame, sizeof fp);
-    Outputs o;
-    o.rgba8 = c->d_rgba8; o.hitq = c->d_hitq; o.hitpix = c->d_hitpix; o.counters = c->d_counters;
-    o.dbg_hit = c->d_dbg_hit; o.dbg_steps = c->d_dbg_steps; o.dbg_occl = c->d_dbg_occl; o.dbg_cast = c->d_dbg_cast;
-    c->launches = 0;
-    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(Counters), c->stream));
-    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     // kernel variants: iteration counting on/off (the step-count view and the debug planes always need it), and the
     // reference's compile-time grid extents (512 x 96 x 512) vs runtime extents
     const bool count = c->count_stats || c->d_dbg_hit != nullptr;
     const bool count_primary = count || c->frame.view_depth_field == 1;
     const bool ref_dims = (g.w == GridViewRef::w && g.h == GridViewRef::h && g.d == GridViewRef::d);
     GridViewRef gr; gr.vox = g.vox;
-    const dim3 grid(c->map.nlocal), block(256);
-    if (ref_dims) {
-        if (count_primary) primary_kernel<true, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, c->map, o);
-        else primary_kernel<false, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, c->map, o);
-    } else {
-        if (count_primary) primary_kernel<true, GridView><<<grid, block, 0, c->stream>>>(g, fp, c->map, o);
-        else primary_kernel<false, GridView><<<grid, block, 0, c->stream>>>(g, fp, c->map, o);
-    }
-    CUDA_TRY(cudaGetLastError());
-    c->launches++;
-    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
-    if (c->frame.view_depth_field != 1) {
-        if (ref_dims) {
-            if (count) shade_kernel<true, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, c->map, o);
-            else shade_kernel<false, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, c->map, o);
-        } else {
-            if (count) shade_kernel<true, GridView><<<grid, block, 0, c->stream>>>(g, fp, c->map, o);
-            else shade_kernel<false, GridView><<<grid, block, 0, c->stream>>>(g, fp, c->map, o);
-        }
+    // bands: whole tile rows when this context owns the whole frame (raster rows stay contiguous), else tile ranges
+    const int units = (c->cfg.world == 1) ? c->map.ty : c->map.nlocal;
+    const int tiles_per_unit = (c->cfg.world == 1) ? c->map.tx : 1;
+    if (nbands > units) nbands = units;
+    if (nbands > MAX_BANDS) nbands = MAX_BANDS;
+    if (nbands < 1) nbands = 1;
+    c->launches = 0;
+    c->bands_used = nbands;
+    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(Counters) * MAX_BANDS, c->stream));
+    if (c->p2p) {
+        if (host_dst) return fail(VXRT_ERR_STATE, "render_frame_host is not available on a peer-memory context: use vxrt_p2p_wait_frame on the owner");
+        p2p_wait_consumed_kernel<<<1, 1, 0, c->stream>>>((const P2PShared*)c->p2p_base, c->p2p_seq, c->d_p2p_err);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
     }
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    for (int b = 0; b < nbands; b++) {
+        const int u0 = (int)((long long)units * b / nbands), u1 = (int)((long long)units * (b + 1) / nbands);
+        const int tile0 = u0 * tiles_per_unit, ntile = (u1 - u0) * tiles_per_unit;
+        if (ntile <= 0) continue;
+        TileMap m = c->map;
+        m.tile_base = tile0;
+        Outputs o;
+        o.rgba8 = c->p2p ? (uint32_t*)(c->p2p_base + sizeof(P2PShared) + (c->p2p_seq & 1) * c->p2p_frame_bytes) : c->d_rgba8;
+        o.raster = (c->cfg.world == 1 || c->p2p) ? 1 : 0;
+        o.hitq = c->d_hitq + (size_t)tile0 * TILE_PIX; o.hitpix = c->d_hitpix + (size_t)tile0 * TILE_PIX;
+        o.counters = c->d_counters + b;
+        o.dbg_hit = c->d_dbg_hit; o.dbg_steps = c->d_dbg_steps; o.dbg_occl = c->d_dbg_occl; o.dbg_cast = c->d_dbg_cast;
+        const dim3 grid(ntile), block(256);
+        if (ref_dims) {
+            if (count_primary) primary_kernel<true, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, m, o);
+            else primary_kernel<false, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, m, o);
+        } else {
+            if (count_primary) primary_kernel<true, GridView><<<grid, block, 0, c->stream>>>(g, fp, m, o);
+            else primary_kernel<false, GridView><<<grid, block, 0, c->stream>>>(g, fp, m, o);
+        }
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+        if (nbands == 1) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        if (c->frame.view_depth_field != 1) {
+            if (ref_dims) {
+                if (count) shade_kernel<true, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, m, o);
+                else shade_kernel<false, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, m, o);
+            } else {
+                if (count) shade_kernel<true, GridView><<<grid, block, 0, c->stream>>>(g, fp, m, o);
+                else shade_kernel<false, GridView><<<grid, block, 0, c->stream>>>(g, fp, m, o);
+            }
+            CUDA_TRY(cudaGetLastError());
+            c->launches++;
+        }
+        if (host_dst) {
+            size_t off, bytes;
+            if (c->cfg.world == 1) {
+                const int y0 = u0 * TILE_H, y1 = (u1 * TILE_H < c->cfg.height) ? u1 * TILE_H : c->cfg.height;
+                off = (size_t)y0 * c->cfg.width * 4; bytes = (size_t)(y1 - y0) * c->cfg.width * 4;
+            } else {
+                off = (size_t)tile0 * TILE_PIX * 4; bytes = (size_t)ntile * TILE_PIX * 4;
+            }
+            CUDA_TRY(cudaEventRecord(c->ev_band[b], c->stream));
+            CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_band[b], 0));
+            CUDA_TRY(cudaMemcpyAsync(host_dst + off, (const uint8_t*)c->d_rgba8 + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+    }
+    if (nbands != 1) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    if (c->p2p) {
+        p2p_signal_done_kernel<<<1, 1, 0, c->stream>>>((P2PShared*)c->p2p_base, c->cfg.rank, c->p2p_seq);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+        c->p2p_seq++;
+    }
+    if (host_dst) {                                       // later work on the main stream must not overwrite pixels in flight
+        CUDA_TRY(cudaEventRecord(c->ev_copy, c->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+    }
     c->rendered = true;
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_render(vxrt_ctx* c) {                                                // main.cpp:59
+    CHECK_CTX(c);
+    return render_bands(c, 1, nullptr);
+}
+
+extern "C" int vxrt_set_readback_bands(vxrt_ctx* c, int nbands) {
+    if (!c) return fail(VXRT_ERR_INVALID, "null context");
+    if (nbands < 1 || nbands > MAX_BANDS) return fail(VXRT_ERR_INVALID, "readback bands must be in [1,16]");
+    c->readback_bands = nbands;
     return VXRT_OK;
 }
 
@@ -524,21 +607,17 @@ extern "C" int vxrt_render_frame_host(vxrt_ctx* c, const vxrt_frame* f, uint8_t*
     if (!out) return fail(VXRT_ERR_INVALID, "render_frame_host: null output");
     int rc = vxrt_set_frame(c, f);
     if (rc != VXRT_OK) return rc;
-    rc = vxrt_render(c);
-    if (rc != VXRT_OK) return rc;
-    // pinned destination (vxrt_host_alloc / cudaHostRegister): DMA straight into it; pageable: stage through the
-    // context's pinned buffer
+    CHECK_CTX(c);
+    // page-locked destination (vxrt_host_alloc / cudaHostRegister): DMA straight into it; pageable: stage through the
+    // context's pinned buffer.  Either way the copy of band b overlaps the kernels of band b+1.
     cudaPointerAttributes attr;
     const bool pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    if (pinned) {
-        CUDA_TRY(cudaMemcpyAsync(out, c->d_rgba8, c->out_pixels * 4, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-    } else {
-        CUDA_TRY(cudaMemcpyAsync(c->h_frame, c->d_rgba8, c->out_pixels * 4, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        memcpy(out, c->h_frame, c->out_pixels * 4);
-    }
+    rc = render_bands(c, c->readback_bands, pinned ? out : c->h_frame);
+    if (rc != VXRT_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (!pinned) memcpy(out, c->h_frame, c->out_pixels * 4);
     return VXRT_OK;
 }
 
@@ -569,9 +648,14 @@ extern "C" int vxrt_get_stats(vxrt_ctx* c, vxrt_stats* out) {
     CHECK_CTX(c);
     if (!out) return fail(VXRT_ERR_INVALID, "get_stats: null output");
     if (!c->rendered) return fail(VXRT_ERR_STATE, "get_stats before render");
-    Counters h;
-    CUDA_TRY(cudaMemcpyAsync(&h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    Counters hb[MAX_BANDS], h;
+    CUDA_TRY(cudaMemcpyAsync(hb, c->d_counters, sizeof hb, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memset(&h, 0, sizeof h);
+    for (int b = 0; b < MAX_BANDS; b++) {
+        h.hit_count += hb[b].hit_count; h.rays_local += hb[b].rays_local;
+        h.fetches_primary += hb[b].fetches_primary; h.fetches_shadow += hb[b].fetches_shadow;
+    }
     memset(out, 0, sizeof *out);
     // pixels this context rendered (padding tiles and clipped pixels excluded)
     uint64_t pix = 0;
@@ -667,6 +751,85 @@ extern "C" size_t vxrt_local_tiles(vxrt_ctx* c) { return c ? (size_t)c->map.nloc
 extern "C" size_t vxrt_local_bytes(vxrt_ctx* c) { return c ? (size_t)c->map.nlocal * TILE_PIX * 4 : 0; }
 extern "C" void* vxrt_device_rgba8(vxrt_ctx* c) { return c ? (void*)c->d_rgba8 : nullptr; }
 extern "C" void* vxrt_stream(vxrt_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// ---- peer-memory frame target ----------------------------------------------------------------------
+extern "C" int vxrt_p2p_export(vxrt_ctx* c, uint8_t handle[64]) {
+    CHECK_CTX(c);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!handle) return fail(VXRT_ERR_INVALID, "p2p_export: null handle");
+    if (c->p2p) return fail(VXRT_ERR_STATE, "peer-memory target already set");
+    if (c->cfg.world > 16) return fail(VXRT_ERR_INVALID, "peer-memory target supports up to 16 ranks");
+    c->p2p_frame_bytes = (size_t)c->cfg.width * c->cfg.height * 4;
+    const size_t total = sizeof(P2PShared) + 2 * c->p2p_frame_bytes;
+    CUDA_TRY(cudaMalloc(&c->p2p_base, total));
+    CUDA_TRY(cudaMemset(c->p2p_base, 0, total));
+    CUDA_TRY(cudaMalloc(&c->d_p2p_err, sizeof(int)));
+    CUDA_TRY(cudaMemset(c->d_p2p_err, 0, sizeof(int)));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, c->p2p_base));
+    memcpy(handle, &h, 64);
+    c->p2p = true; c->p2p_owner = true; c->p2p_seq = 0;
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_p2p_import(vxrt_ctx* c, const uint8_t handle[64]) {
+    CHECK_CTX(c);
+    if (!handle) return fail(VXRT_ERR_INVALID, "p2p_import: null handle");
+    if (c->p2p) return fail(VXRT_ERR_STATE, "peer-memory target already set");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->p2p_base = (uint8_t*)p;
+    c->p2p_frame_bytes = (size_t)c->cfg.width * c->cfg.height * 4;
+    CUDA_TRY(cudaMalloc(&c->d_p2p_err, sizeof(int)));
+    CUDA_TRY(cudaMemset(c->d_p2p_err, 0, sizeof(int)));
+    c->p2p = true; c->p2p_owner = false; c->p2p_seq = 0;
+    return VXRT_OK;
+}
+
+// same-process variant of import (several contexts in one process, peer access enabled between their devices)
+extern "C" int vxrt_p2p_attach(vxrt_ctx* c, void* owner_base) {
+    CHECK_CTX(c);
+    if (!owner_base) return fail(VXRT_ERR_INVALID, "p2p_attach: null base");
+    if (c->p2p) return fail(VXRT_ERR_STATE, "peer-memory target already set");
+    c->p2p_base = (uint8_t*)owner_base;
+    c->p2p_frame_bytes = (size_t)c->cfg.width * c->cfg.height * 4;
+    CUDA_TRY(cudaMalloc(&c->d_p2p_err, sizeof(int)));
+    CUDA_TRY(cudaMemset(c->d_p2p_err, 0, sizeof(int)));
+    c->p2p = true; c->p2p_owner = false; c->p2p_attached = true; c->p2p_seq = 0;
+    return VXRT_OK;
+}
+extern "C" void* vxrt_p2p_base(vxrt_ctx* c) { return (c && c->p2p) ? (void*)c->p2p_base : nullptr; }
+
+extern "C" int vxrt_p2p_wait_frame(vxrt_ctx* c, void** frame) {
+    CHECK_CTX(c);
+    if (!c->p2p || !c->p2p_owner) return fail(VXRT_ERR_STATE, "p2p_wait_frame: not the owner of a peer-memory target");
+    if (c->p2p_seq == 0) return fail(VXRT_ERR_STATE, "p2p_wait_frame before render");
+    const unsigned long long seq = c->p2p_seq - 1;
+    p2p_wait_done_kernel<<<1, 32, 0, c->stream>>>((const P2PShared*)c->p2p_base, c->cfg.world, seq, c->d_p2p_err);
+    CUDA_TRY(cudaGetLastError());
+    if (frame) *frame = c->p2p_base + sizeof(P2PShared) + (seq & 1) * c->p2p_frame_bytes;
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_p2p_release_frame(vxrt_ctx* c) {
+    CHECK_CTX(c);
+    if (!c->p2p || !c->p2p_owner) return fail(VXRT_ERR_STATE, "p2p_release_frame: not the owner of a peer-memory target");
+    if (c->p2p_seq == 0) return fail(VXRT_ERR_STATE, "p2p_release_frame before render");
+    p2p_release_kernel<<<1, 1, 0, c->stream>>>((P2PShared*)c->p2p_base, c->p2p_seq - 1);
+    CUDA_TRY(cudaGetLastError());
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_p2p_error(vxrt_ctx* c) {
+    CHECK_CTX(c);
+    if (!c->p2p) return 0;
+    int e = 0;
+    CUDA_TRY(cudaMemcpyAsync(&e, c->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return e;
+}
 
 extern "C" int vxrt_assemble_tiles(vxrt_ctx* c, const void* gathered, void* dst, void* stream) {
     CHECK_CTX(c);
