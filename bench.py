@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C3ii_4k", choices=sorted(WORKLOADS))
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: 'p2p' = kernels store straight into rank 0's frame over NVLink (no collective); "
+                         "'nccl' = all-gather of tile buffers + un-tile kernel")
+    ap.add_argument("--bands", type=int, default=4, help="read-back bands of vxrt_render_frame_host (e2e, N = 1)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads / cpu baseline (profiling runs)")
     return ap.parse_args()
 
@@ -176,10 +180,20 @@ def run_b200(args):
     edits = vx.scenes.edit_centres(1000) if scene == "C5" else None
     edit_state = {"k": 0}
 
+    ren.setReadbackBands(args.bands)
+    use_p2p = world > 1 and args.exchange == "p2p"
     stream = torch.cuda.ExternalStream(ren.stream_ptr(), device=torch.device("cuda", local_rank))
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
     local_bytes = ren.local_bytes()
-    if world > 1:
+    if use_p2p:
+        handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            handle.copy_(torch.from_numpy(ren.p2pExport()))
+        dist.broadcast(handle, src=0)
+        if rank != 0:
+            ren.p2pImport(handle.cpu().numpy())
+        gathered = final = local_t = None
+    elif world > 1:
         local_t = torch.empty(0)                                  # placeholder; real tensors below
         gathered = torch.empty(world * local_bytes, dtype=torch.uint8, device="cuda")
         final = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
@@ -192,10 +206,17 @@ def run_b200(args):
         """one frame with inputs resident: kernels (+ gather + un-tile for N > 1) on the renderer's stream"""
         apply_edit()
         ren.draw()
-        if world > 1:
+        if use_p2p:
+            if rank == 0:                                         # owner: acquire every rank's completion flag, then release
+                p2p_state["ptr"] = ren.p2pWaitFrame()
+                if not p2p_state["hold"]:
+                    ren.p2pReleaseFrame()
+        elif world > 1:
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(gathered, local_t)
             ren.assembleTiles(gathered.data_ptr(), final.data_ptr())
+
+    p2p_state = {"ptr": 0, "hold": False}
 
     def apply_edit():
         if edits is not None:                                     # C5: right-click destruction before every frame
@@ -277,6 +298,18 @@ def run_b200(args):
         if world == 1:
             apply_edit()
             ren.renderFrameHost(frame, host_out)                  # set_frame + kernels + D2H into page-locked memory + sync
+        elif use_p2p:
+            ren.updateUniforms(frame)
+            p2p_state["hold"] = True                              # keep the frame until it has been copied out
+            step_device()
+            p2p_state["hold"] = False
+            if rank == 0:
+                class _F:
+                    __cuda_array_interface__ = {"shape": (H, W, 4), "typestr": "|u1", "data": (p2p_state["ptr"], False), "version": 3}
+                with torch.cuda.stream(stream):
+                    final_host.copy_(torch.as_tensor(_F(), device="cuda"), non_blocking=True)
+                ren.p2pReleaseFrame()
+            ren.sync()
         else:
             ren.updateUniforms(frame)
             step_device()
@@ -329,13 +362,15 @@ def run_b200(args):
                        "setup": build_info,
                        "view_depth_field": int(frame.view_depth_field), "rays_per_frame": rays, "rays_primary": rp, "rays_global": rg,
                        "rays_local": rl, "voxel_fetches_per_frame": fetches, "hit_pixels": hits,
-                       "partition": "sort-first 32x8 tiles, tile t -> rank t %% %d, grid replicated, NCCL all-gather of RGBA8 tiles" % world,
+                       "partition": "sort-first 32x8 tiles, tile t -> rank t %% %d, grid replicated; frame exchange: %s" % (
+                           world, "none (1 GPU)" if world == 1 else ("kernels store into rank 0's frame over NVLink peer memory, release/acquire flags" if use_p2p
+                                                                     else "NCCL all-gather of RGBA8 tiles + un-tile kernel")),
                        "l2": "flushed between timed frames (256 MiB write)", "timing": "CUDA events on the launching stream per frame, max over ranks"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "vxrt_render_frame_host (C ABI): host frame params in, host RGBA8 frame out; wall clock"},
-            "gpu_launches": int(args.steps * (2 + (1 if world > 1 else 0))),
+            "gpu_launches": int(args.steps * (2 + ((3 if use_p2p else 1) if world > 1 else 0))),
             "roofline": roofline,
             "wall_s_timed_region": round(t_wall, 3),
         }
@@ -351,6 +386,9 @@ def run_b200(args):
         dist.destroy_process_group()
         del gathered, final, local_t
     del flush, final_host
+    p2p_err = ren.p2pError() if use_p2p else 0
+    if p2p_err:
+        raise SystemExit("peer-memory wait timed out (code %d)" % p2p_err)
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     ren.close()

@@ -1,0 +1,45 @@
+"""Kernel experiment harness: times the frame kernels of one libvxrt build (VXRT_LIB=path selects it).
+    VXRT_LIB=/tmp/x.so python scripts/exp_time.py [--frames 30] [--workloads C3ii_4k,C3i_4k]
+Prints per workload: primary / shade / total ms (CUDA events inside vxrt_render, counters off, L2 flushed)."""
+import argparse
+import os
+import statistics
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch                      # noqa: E402
+import voxel_rt_b200 as vx        # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--frames", type=int, default=30)
+ap.add_argument("--workloads", default="C3ii_4k,C3i_4k,C2_1080p")
+a = ap.parse_args()
+W0, H0 = 3840, 2160
+ren = vx.Renderer(grid=vx.scenes.DEFAULT_GRID, width=W0, height=H0)
+ren.initVoxels(); ren.buildDepthField()
+assert vx.scenes.fnv1a64(ren.downloadGrid()) == 0x4c58cc4001a22afa
+stream = torch.cuda.ExternalStream(ren.stream_ptr())
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for wl in a.workloads.split(","):
+    scene, res = wl.rsplit("_", 1)
+    W, H = vx.scenes.RESOLUTIONS[res]
+    if (W, H) != (ren.width, ren.height):
+        ren.reshape(W, H)
+    ren.updateUniforms(vx.scenes.frame_for(scene, W, H))
+    ren.setStats(True); ren.draw(); st = ren.stats(); rays = vx.scenes.total_rays(st)
+    ren.setStats(False)
+    for _ in range(20):
+        ren.draw()
+    ren.sync()
+    p, s, t = [], [], []
+    for _ in range(a.frames):
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+        ren.draw()
+        x = ren.stats()
+        p.append(x["ms_primary"]); s.append(x["ms_shadow"]); t.append(x["ms_total"])
+    m = statistics.mean(t)
+    print("%-14s primary %.4f  shade %.4f  total %.4f ms  (min %.4f)  %.1f Mrays/s" % (wl, statistics.mean(p), statistics.mean(s), m, min(t), rays / m / 1e3))
+del flush
+torch.cuda.synchronize()
+ren.close()

@@ -45,14 +45,50 @@ def main():
         ren.sync()
         return final.cpu().numpy()
 
+    # ---- gather-free variant: a second context per rank whose kernels store straight into rank 0's frame ----
+    ren2 = vx.Renderer(grid=vx.scenes.DEFAULT_GRID, width=W, height=H, device=local, rank=rank, world=world)
+    ren2.initVoxels()
+    ren2.buildDepthField()
+    handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        handle.copy_(torch.from_numpy(ren2.p2pExport()))
+    dist.broadcast(handle, src=0)
+    if rank != 0:
+        ren2.p2pImport(handle.cpu().numpy())
+    stream2 = torch.cuda.ExternalStream(ren2.stream_ptr(), device=torch.device("cuda", local))
+    final2 = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
+
+    def render_frame_p2p(nframes=1):
+        out = None
+        for _ in range(nframes):
+            ren2.updateUniforms(frame)
+            ren2.draw()
+            if rank == 0:
+                ptr = ren2.p2pWaitFrame()
+
+                class _F:
+                    __cuda_array_interface__ = {"shape": (H, W, 4), "typestr": "|u1", "data": (ptr, False), "version": 3}
+                with torch.cuda.stream(stream2):
+                    final2.copy_(torch.as_tensor(_F(), device="cuda"))
+                ren2.p2pReleaseFrame()
+        ren2.sync()
+        if rank == 0:
+            out = final2.cpu().numpy()
+        dist.barrier()
+        return out
+
     ok = True
     got = render_frame()
+    got_p2p = render_frame_p2p(5)                  # 5 frames > 2 buffers: exercises the back-pressure across processes
     # edit broadcast: rank 0 picks the edits, every replica applies the same commands
     edits = torch.tensor(vx.scenes.edit_centres(8) if rank == 0 else np.zeros((8, 3), np.int32), dtype=torch.int32, device="cuda")
     dist.broadcast(edits, src=0)
     for c in edits.cpu().numpy():
         ren.removeSphere(c, 7)
+        ren2.removeSphere(c, 7)
     got_edit = render_frame()
+    got_edit_p2p = render_frame_p2p(3)
+    p2p_err = ren2.p2pError()
     fnv = vx.scenes.fnv1a64(ren.downloadGrid())
     fnvs = [None] * world
     dist.all_gather_object(fnvs, fnv)
@@ -67,19 +103,24 @@ def main():
         want = o.render(level, (512, 96, 512), fr, W, H)["rgba8"]
         ok &= bool(np.array_equal(got, want))
         print("frame vs oracle:", np.array_equal(got, want))
+        ok &= bool(np.array_equal(got_p2p, want))
+        print("peer-memory frame vs oracle:", np.array_equal(got_p2p, want))
         for c in vx.scenes.edit_centres(8):
             o.remove_sphere(level, (512, 96, 512), int(c[0]), int(c[1]), int(c[2]), 7)
         want2 = o.render(level, (512, 96, 512), fr, W, H)["rgba8"]
         ok &= bool(np.array_equal(got_edit, want2))
         print("frame after broadcast edits vs oracle:", np.array_equal(got_edit, want2))
+        ok &= bool(np.array_equal(got_edit_p2p, want2)) and p2p_err == 0
+        print("peer-memory frame after edits vs oracle:", np.array_equal(got_edit_p2p, want2), "p2p_err", p2p_err)
         ok &= all(f == o.fnv(level) for f in fnvs)
         print("replica fingerprints equal oracle:", all(f == o.fnv(level) for f in fnvs), ["%016x" % f for f in fnvs])
     dist.barrier()
     dist.destroy_process_group()
-    del gathered, final, local_t
+    del gathered, final, local_t, final2, handle
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     ren.close()
+    ren2.close()
     if rank == 0:
         print("MULTIGPU CHECK", "PASS" if ok else "FAIL")
         sys.exit(0 if ok else 1)

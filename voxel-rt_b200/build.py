@@ -36,10 +36,13 @@ def build_host(force=False):
 
 
 def lib_path():
-    return LIB
+    """VXRT_LIB overrides the in-tree library (kernel experiments: scripts/exp_time.py)"""
+    return os.environ.get("VXRT_LIB", LIB)
 
 
 def needs_build():
+    if os.environ.get("VXRT_LIB"):
+        return False
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
