@@ -40,6 +40,26 @@ for wl in a.workloads.split(","):
         p.append(x["ms_primary"]); s.append(x["ms_shadow"]); t.append(x["ms_total"])
     m = statistics.mean(t)
     print("%-14s primary %.4f  shade %.4f  total %.4f ms  (min %.4f)  %.1f Mrays/s" % (wl, statistics.mean(p), statistics.mean(s), m, min(t), rays / m / 1e3))
+# end-to-end (host frame params in, host RGBA8 out) vs read-back band count, 4K / 16 lights
+import time
+W, H = vx.scenes.RESOLUTIONS["4k"]
+if (W, H) != (ren.width, ren.height):
+    ren.reshape(W, H)
+fr = vx.scenes.frame_for("C3ii", W, H)
+out = ren.hostFrameBuffer()
+for nb in (1, 2, 4, 6, 8, 12, 16):
+    ren.setReadbackBands(nb)
+    for _ in range(5):
+        ren.renderFrameHost(fr, out)
+    ts = []
+    for _ in range(a.frames):
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+        ren.sync()
+        t0 = time.perf_counter()
+        ren.renderFrameHost(fr, out)
+        ts.append(time.perf_counter() - t0)
+    print("e2e bands=%2d  mean %.4f ms  min %.4f ms" % (nb, 1e3 * statistics.mean(ts), 1e3 * min(ts)))
 del flush
 torch.cuda.synchronize()
 ren.close()

@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(256) shade_kernel(Grid g, const __grid_constan
                                           __fadd_rn(hz, __fmul_rn(tz, 0.001f)), tx, ty, tz, f2i(__fadd_rn(lld, 1.0f)));   // :175
                 fetches += (unsigned)s.steps;
                 if (s.idx == -1) {                                                          // :177
-                    const float fall = __fdiv_rn(__fsub_rn((float)VXRT_LOCAL_LIGHT_DIST, lld), (float)VXRT_LOCAL_LIGHT_DIST);
+                    // (64 - d) / 64: dividing by a power of two is an exact scaling, identical to the IEEE quotient
+                    const float fall = __fmul_rn(__fsub_rn((float)VXRT_LOCAL_LIGHT_DIST, lld), 1.0f / (float)VXRT_LOCAL_LIGHT_DIST);
                     multiplier = __fadd_rn(multiplier, __fmul_rn(__fmul_rn(L.w, max0(dot3(nx, ny, nz, tx, ty, tz))), fall));
                 } else occl |= 2u << slot;
             }
