@@ -143,7 +143,13 @@ int vxrt_set_stats(vxrt_ctx* ctx, int enabled);
    world > 1: out receives this rank's tiles in gather layout (vxrt_local_bytes()). */
 int vxrt_render_frame_host(vxrt_ctx* ctx, const vxrt_frame* frame, uint8_t* out);
 
-/* vxrt_render_frame_host renders the frame in `nbands` bands of tile rows (default 4, 1..16) and copies each band
+/* Pipelined form of vxrt_render_frame_host for a stream of frames: queues set_frame + render + read-back into the
+   page-locked buffer `out` and returns; frames alternate between two device buffers so that the read-back of one
+   frame overlaps the kernels of the next.  `out` may be reused once vxrt_wait_frames returned (or two submits later).
+   vxrt_wait_frames blocks until every submitted frame is complete in host memory. */
+int vxrt_submit_frame_host(vxrt_ctx* ctx, const vxrt_frame* frame, uint8_t* out);
+int vxrt_wait_frames(vxrt_ctx* ctx);
+/* vxrt_render_frame_host renders the frame in `nbands` bands of tile rows (default 2, 1..16) and copies each band
    to the host while the next one renders.  Same pixels for every value. */
 int vxrt_set_readback_bands(vxrt_ctx* ctx, int nbands);
 

@@ -172,6 +172,25 @@ def test_banded_readback_renders_the_same_frame(vx, oracle, default_level, size)
     assert np.array_equal(vx.tiles.assemble(np.stack(parts), W, H), want)
 
 
+def test_pipelined_frame_submission(vx, oracle, default_level):
+    """vxrt_submit_frame_host: a stream of different frames, read-back of frame k overlapping the kernels of k+1,
+    two device buffers / two host buffers; every frame must arrive intact"""
+    W, H = 416, 240
+    names = ["C2", "C3ii_pitched", "C3i", "sparse_lights", "C1", "low_sun", "C2"]
+    with vx.Renderer(grid=gc.DIMS, width=W, height=H) as r:
+        r.updateGeometry(default_level)
+        bufs = [r.hostFrameBuffer() for _ in range(len(names))]
+        for k, name in enumerate(names):
+            r.submitFrameHost(to_vx_frame(vx, gc.frame_cases(W, H)[name]), bufs[k])
+        r.waitFrames()
+        for k, name in enumerate(names):
+            assert np.array_equal(bufs[k], oracle.render(default_level, gc.DIMS, gc.frame_cases(W, H)[name], W, H)["rgba8"]), (k, name)
+        with pytest.raises(vx.VxrtError, match="page-locked"):
+            r.submitFrameHost(to_vx_frame(vx, gc.frame_cases(W, H)["C1"]), np.empty((H, W, 4), np.uint8))
+        # synchronous calls still work afterwards
+        assert np.array_equal(r.renderFrameHost(to_vx_frame(vx, gc.frame_cases(W, H)["C1"])), bufs[4])
+
+
 def test_render_is_idempotent_and_view_toggle(vx, ren):
     W, H = 160, 90
     ren.reshape(W, H)

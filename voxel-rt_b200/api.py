@@ -75,6 +75,8 @@ _SIGNATURES = {
     "vxrt_set_readback_bands": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_render_frame_host": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p]),
+    "vxrt_submit_frame_host": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p]),
+    "vxrt_wait_frames": (C.c_int, [C.c_void_p]),
     "vxrt_read_rgba8": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vxrt_read_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vxrt_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
@@ -312,6 +314,13 @@ class Renderer:
             out = np.empty(self.out_shape(), np.uint8)
         self._check(self.lib.vxrt_render_frame_host(self._h, C.byref(frame), _vp(out)))
         return out
+
+    def submitFrameHost(self, frame, out):
+        """pipelined renderFrameHost: queue the frame, read-back overlaps the next frame's kernels; `out` from hostFrameBuffer()"""
+        self._check(self.lib.vxrt_submit_frame_host(self._h, C.byref(frame), _vp(out)))
+
+    def waitFrames(self):
+        self._check(self.lib.vxrt_wait_frames(self._h))
 
     def readPixels(self):
         out = np.empty(self.out_shape(), np.uint8)

@@ -36,7 +36,12 @@ struct vxrt_ctx {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_band[MAX_BANDS] = {};
     cudaEvent_t ev_copy = nullptr;
-    int readback_bands = 4;
+    int readback_bands = 2;
+    // pipelined read-back (vxrt_submit_frame_host): second device frame + per-slot "copy finished" events
+    uint32_t* d_rgba8_alt = nullptr;
+    cudaEvent_t ev_slot[2] = {nullptr, nullptr};
+    bool slot_busy[2] = {false, false};
+    unsigned long long submit_seq = 0;
     // grid
     int32_t* d_vox = nullptr;
     size_t nvox = 0;
@@ -94,7 +99,8 @@ static GridView grid_view(const vxrt_ctx* c) {
 }
 
 static void free_frame_buffers(vxrt_ctx* c) {
-    cudaFree(c->d_rgba8); cudaFree(c->d_hitq); cudaFree(c->d_hitpix);
+    cudaFree(c->d_rgba8); cudaFree(c->d_rgba8_alt); cudaFree(c->d_hitq); cudaFree(c->d_hitpix);
+    c->d_rgba8_alt = nullptr; c->slot_busy[0] = c->slot_busy[1] = false;
     cudaFree(c->d_dbg_hit); cudaFree(c->d_dbg_steps); cudaFree(c->d_dbg_occl); cudaFree(c->d_dbg_cast);
     c->d_rgba8 = nullptr; c->d_hitq = nullptr; c->d_hitpix = nullptr;
     c->d_dbg_hit = nullptr; c->d_dbg_steps = nullptr; c->d_dbg_occl = nullptr; c->d_dbg_cast = nullptr;
@@ -239,6 +245,7 @@ extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaStreamCreate failed"));
     for (auto& e : c->ev_band) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
     if (cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
+    for (auto& e : c->ev_slot) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
     if (cudaMalloc(&c->d_counters, sizeof(Counters) * MAX_BANDS) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaMalloc(counters) failed"));
     int rc = upload_depth_offsets();
     if (rc != VXRT_OK) return bail(rc);
@@ -268,6 +275,7 @@ extern "C" void vxrt_destroy(vxrt_ctx* c) {
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_band) if (e) cudaEventDestroy(e);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    for (auto& e : c->ev_slot) if (e) cudaEventDestroy(e);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -489,7 +497,11 @@ extern "C" int vxrt_resize(vxrt_ctx* c, int width, int height) {                
 // Launches the frame's kernels in `nbands` bands of whole tile rows.  host_dst != nullptr: each band's pixels are
 // copied to host_dst (page-locked) on the copy stream as soon as the band's kernels finish, so the read-back of
 // band b overlaps the rendering of band b+1.
-static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst) {
+static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* dev_out = nullptr, bool fence_main = true) {
+    if (!dev_out) dev_out = c->d_rgba8;
+    if (fence_main)                                       // synchronous paths: never overwrite a frame a pipelined copy still reads
+        for (int slot = 0; slot < 2; slot++)
+            if (c->slot_busy[slot]) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_slot[slot], 0));
     if (!c->grid_loaded) return fail(VXRT_ERR_STATE, "render before any grid upload");
     const GridView g = grid_view(c);
     FrameParams fp;
@@ -523,7 +535,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst) {
         TileMap m = c->map;
         m.tile_base = tile0;
         Outputs o;
-        o.rgba8 = c->p2p ? (uint32_t*)(c->p2p_base + sizeof(P2PShared) + (c->p2p_seq & 1) * c->p2p_frame_bytes) : c->d_rgba8;
+        o.rgba8 = c->p2p ? (uint32_t*)(c->p2p_base + sizeof(P2PShared) + (c->p2p_seq & 1) * c->p2p_frame_bytes) : dev_out;
         o.raster = (c->cfg.world == 1 || c->p2p) ? 1 : 0;
         o.hitq = c->d_hitq + (size_t)tile0 * TILE_PIX; o.hitpix = c->d_hitpix + (size_t)tile0 * TILE_PIX;
         o.counters = c->d_counters + b;
@@ -560,7 +572,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst) {
             }
             CUDA_TRY(cudaEventRecord(c->ev_band[b], c->stream));
             CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_band[b], 0));
-            CUDA_TRY(cudaMemcpyAsync(host_dst + off, (const uint8_t*)c->d_rgba8 + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+            CUDA_TRY(cudaMemcpyAsync(host_dst + off, (const uint8_t*)dev_out + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
         }
     }
     if (nbands != 1) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -571,7 +583,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst) {
         c->launches++;
         c->p2p_seq++;
     }
-    if (host_dst) {                                       // later work on the main stream must not overwrite pixels in flight
+    if (host_dst && fence_main) {                         // later work on the main stream must not overwrite pixels in flight
         CUDA_TRY(cudaEventRecord(c->ev_copy, c->copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
     }
@@ -618,6 +630,41 @@ extern "C" int vxrt_render_frame_host(vxrt_ctx* c, const vxrt_frame* f, uint8_t*
     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (!pinned) memcpy(out, c->h_frame, c->out_pixels * 4);
+    return VXRT_OK;
+}
+
+// Pipelined variant: returns as soon as the work is queued.  Frames alternate between two device buffers, so the
+// read-back of frame k (copy stream) overlaps the kernels of frame k+1 (main stream); at most two frames are in
+// flight -- a third submit first waits for the oldest one's copy.  `out` must be page-locked (vxrt_host_alloc).
+extern "C" int vxrt_submit_frame_host(vxrt_ctx* c, const vxrt_frame* f, uint8_t* out) {
+    if (!out) return fail(VXRT_ERR_INVALID, "submit_frame_host: null output");
+    int rc = vxrt_set_frame(c, f);
+    if (rc != VXRT_OK) return rc;
+    CHECK_CTX(c);
+    if (c->p2p) return fail(VXRT_ERR_STATE, "submit_frame_host is not available on a peer-memory context");
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned) return fail(VXRT_ERR_INVALID, "submit_frame_host needs a page-locked destination (vxrt_host_alloc)");
+    if (!c->d_rgba8_alt) CUDA_TRY(cudaMalloc(&c->d_rgba8_alt, c->out_pixels * 4));
+    const int slot = (int)(c->submit_seq & 1);
+    if (c->slot_busy[slot]) {                              // the device buffer of this slot is still being copied out
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_slot[slot], 0));
+    }
+    rc = render_bands(c, 1, out, slot ? c->d_rgba8_alt : c->d_rgba8, /*fence_main=*/false);
+    if (rc != VXRT_OK) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev_slot[slot], c->copy_stream));
+    c->slot_busy[slot] = true;
+    c->submit_seq++;
+    return VXRT_OK;
+}
+
+// blocks until every submitted frame is in host memory
+extern "C" int vxrt_wait_frames(vxrt_ctx* c) {
+    CHECK_CTX(c);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    c->slot_busy[0] = c->slot_busy[1] = false;
     return VXRT_OK;
 }
 
