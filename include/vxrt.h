@@ -135,6 +135,9 @@ int vxrt_resize(vxrt_ctx* ctx, int width, int height);
 /* glDrawArrays(GL_TRIANGLES,0,6) main.cpp:59: runs the per-pixel path for this context's tiles; asynchronous */
 int vxrt_render(vxrt_ctx* ctx);
 int vxrt_sync(vxrt_ctx* ctx);
+/* enabled (default): the primary pass records how long each tile's block took and the next frame launches the
+   slowest tiles first (shorter kernel tail; it matters when a GPU renders only a fraction of the frame).  Same pixels. */
+int vxrt_set_tile_ordering(vxrt_ctx* ctx, int enabled);
 /* enabled (default): every vxrt_render maintains the fetch / local-ray counters of vxrt_stats.  Disabled: the
    kernels skip the per-iteration counter (rays_local / fetches read back as 0; hit_pixels, rays_primary,
    rays_global and the timings stay valid).  Same pixels either way. */
@@ -198,6 +201,10 @@ int vxrt_p2p_attach(vxrt_ctx* ctx, void* owner_base);
 void* vxrt_p2p_base(vxrt_ctx* ctx);
 int vxrt_p2p_wait_frame(vxrt_ctx* ctx, void** frame);
 int vxrt_p2p_release_frame(vxrt_ctx* ctx);
+/* owner, instead of wait_frame / release_frame when the consumer is host memory: queues acquire -> device-to-host copy
+   into the page-locked buffer `out` -> release on the context's copy stream and returns, so the next frame renders
+   while this one is read back; vxrt_wait_frames blocks until the copies are complete */
+int vxrt_p2p_readback(vxrt_ctx* ctx, uint8_t* out);
 int vxrt_p2p_error(vxrt_ctx* ctx);
 
 #ifdef __cplusplus

@@ -13,6 +13,7 @@ import voxel_rt_b200 as vx        # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=30)
 ap.add_argument("--workloads", default="C3ii_4k,C3i_4k,C2_1080p")
+ap.add_argument("--e2e", action="store_true", help="also sweep the read-back band count of the end-to-end call")
 a = ap.parse_args()
 W0, H0 = 3840, 2160
 ren = vx.Renderer(grid=vx.scenes.DEFAULT_GRID, width=W0, height=H0)
@@ -47,7 +48,7 @@ if (W, H) != (ren.width, ren.height):
     ren.reshape(W, H)
 fr = vx.scenes.frame_for("C3ii", W, H)
 out = ren.hostFrameBuffer()
-for nb in (1, 2, 4, 6, 8, 12, 16):
+for nb in ((1, 2, 4, 6, 8, 12, 16) if a.e2e else ()):
     ren.setReadbackBands(nb)
     for _ in range(5):
         ren.renderFrameHost(fr, out)

@@ -1,4 +1,4 @@
 set -x
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python scripts/exp_time.py 2>&1 | tail -4
+python scripts/exp_time.py 2>&1 | tail -12

@@ -88,6 +88,16 @@ def main():
         ren2.removeSphere(c, 7)
     got_edit = render_frame()
     got_edit_p2p = render_frame_p2p(3)
+    # pipelined owner read-back: 6 frames queued back to back, alternating host buffers
+    bufs = [ren2.hostFrameBuffer(full_frame=True), ren2.hostFrameBuffer(full_frame=True)] if rank == 0 else None
+    for k in range(6):
+        ren2.updateUniforms(frame)
+        ren2.draw()
+        if rank == 0:
+            ren2.p2pReadback(bufs[k & 1])
+    ren2.waitFrames()
+    dist.barrier()
+    readback_ok = bool(np.array_equal(bufs[0], got_edit_p2p) and np.array_equal(bufs[1], got_edit_p2p)) if rank == 0 else True
     p2p_err = ren2.p2pError()
     fnv = vx.scenes.fnv1a64(ren.downloadGrid())
     fnvs = [None] * world
@@ -112,6 +122,8 @@ def main():
         print("frame after broadcast edits vs oracle:", np.array_equal(got_edit, want2))
         ok &= bool(np.array_equal(got_edit_p2p, want2)) and p2p_err == 0
         print("peer-memory frame after edits vs oracle:", np.array_equal(got_edit_p2p, want2), "p2p_err", p2p_err)
+        ok &= readback_ok
+        print("pipelined peer-memory read-back frames intact:", readback_ok)
         ok &= all(f == o.fnv(level) for f in fnvs)
         print("replica fingerprints equal oracle:", all(f == o.fnv(level) for f in fnvs), ["%016x" % f for f in fnvs])
     dist.barrier()

@@ -202,8 +202,25 @@ def test_render_is_idempotent_and_view_toggle(vx, ren):
     c = ren.renderFrameHost(fr)
     assert np.array_equal(c[..., 0], c[..., 1]) and np.array_equal(c[..., 1], c[..., 2]) and (c[..., 3] == 255).all()
     assert ren.stats()["rays_local"] == 0 and ren.stats()["kernel_launches"] == ren.stats()["kernel_launches"] >= 1
+    ren.setTileOrdering(False)
     ren.draw()
     assert ren.stats()["kernel_launches"] == 1                      # step-count view: the primary kernel only
+    ren.setTileOrdering(True)
+    ren.draw(); ren.draw()
+    assert ren.stats()["kernel_launches"] in (1, 2)                 # + the tile-order kernel (frames of >= 64 tiles)
+    assert np.array_equal(ren.readPixels(), c)                      # launch order does not change pixels
+    ren.reshape(640, 360)                                            # 900 tiles: ordering active from the second frame on
+    fr2 = to_vx_frame(vx, gc.frame_cases(640, 360)["C3ii_pitched"])
+    ren.setTileOrdering(False)
+    want = ren.renderFrameHost(fr2)
+    ren.setTileOrdering(True)
+    ren.updateUniforms(fr2)
+    launches = []
+    for _ in range(10):
+        ren.draw()
+        launches.append(ren.stats()["kernel_launches"])
+        assert np.array_equal(ren.readPixels(), want)
+    assert launches[0] == 4 and launches[1] == 4 and launches[2] == 2 and launches[8] == 4     # orders refreshed on frames 0, 1, 8, ...
 
 
 # ---- other grid shapes ---------------------------------------------------------------------------
@@ -411,6 +428,18 @@ def test_peer_memory_frame_target_protocol_on_one_gpu(vx, oracle, default_level)
             ctxs[0].p2pReleaseFrame()
             ctxs[0].sync()
             assert np.array_equal(out.cpu().numpy(), oracle.render(default_level, gc.DIMS, fr, W, H)["rgba8"]), name
+        # pipelined owner read-back: acquire -> D2H -> release on the copy stream, next frame already rendering
+        bufs = [ctxs[0].hostFrameBuffer(full_frame=True) for _ in range(2)]
+        seq = ["C2", "C3ii_pitched", "C2", "C3ii_pitched", "C2", "C3ii_pitched"]
+        for k, name in enumerate(seq):
+            for r in ctxs:
+                r.updateUniforms(to_vx_frame(vx, gc.frame_cases(W, H)[name]))
+                r.draw()
+            ctxs[0].p2pReadback(bufs[k & 1])
+        for r in ctxs:
+            r.waitFrames()
+        assert np.array_equal(bufs[0], oracle.render(default_level, gc.DIMS, gc.frame_cases(W, H)["C2"], W, H)["rgba8"])
+        assert np.array_equal(bufs[1], oracle.render(default_level, gc.DIMS, gc.frame_cases(W, H)["C3ii_pitched"], W, H)["rgba8"])
         assert all(r.p2pError() == 0 for r in ctxs)
         with pytest.raises(vx.VxrtError):
             ctxs[1].p2pWaitFrame()                                             # only the owner may wait

@@ -73,6 +73,7 @@ _SIGNATURES = {
     "vxrt_render": (C.c_int, [C.c_void_p]),
     "vxrt_sync": (C.c_int, [C.c_void_p]),
     "vxrt_set_readback_bands": (C.c_int, [C.c_void_p, C.c_int]),
+    "vxrt_set_tile_ordering": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_render_frame_host": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p]),
     "vxrt_submit_frame_host": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p]),
@@ -93,6 +94,7 @@ _SIGNATURES = {
     "vxrt_p2p_base": (C.c_void_p, [C.c_void_p]),
     "vxrt_p2p_wait_frame": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "vxrt_p2p_release_frame": (C.c_int, [C.c_void_p]),
+    "vxrt_p2p_readback": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vxrt_p2p_error": (C.c_int, [C.c_void_p]),
     "vxrt_assemble_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
@@ -281,6 +283,9 @@ class Renderer:
         """glDrawArrays(GL_TRIANGLES,0,6) main.cpp:59 (asynchronous)."""
         self._check(self.lib.vxrt_render(self._h))
 
+    def setTileOrdering(self, enabled):
+        self._check(self.lib.vxrt_set_tile_ordering(self._h, 1 if enabled else 0))
+
     def setStats(self, enabled):
         """fetch / local-ray counters on (default) or off (production frames: one issue slot less per DDA iteration)"""
         self._check(self.lib.vxrt_set_stats(self._h, 1 if enabled else 0))
@@ -298,9 +303,9 @@ class Renderer:
     def out_shape(self):
         return (self.height, self.width, 4) if self.world == 1 else (self.local_bytes() // (TILE_W * TILE_H * 4), TILE_H, TILE_W, 4)
 
-    def hostFrameBuffer(self):
+    def hostFrameBuffer(self, full_frame=False):
         """page-locked numpy frame buffer (vxrt_host_alloc) for renderFrameHost; freed with the renderer"""
-        shape = self.out_shape()
+        shape = (self.height, self.width, 4) if full_frame else self.out_shape()
         n = int(np.prod(shape))
         p = self.lib.vxrt_host_alloc(n)
         if not p:
@@ -391,6 +396,10 @@ class Renderer:
 
     def p2pReleaseFrame(self):
         self._check(self.lib.vxrt_p2p_release_frame(self._h))
+
+    def p2pReadback(self, out):
+        """owner rank: queue acquire -> D2H into the page-locked `out` -> release; returns immediately"""
+        self._check(self.lib.vxrt_p2p_readback(self._h, _vp(out)))
 
     def p2pError(self):
         return self._check(self.lib.vxrt_p2p_error(self._h))

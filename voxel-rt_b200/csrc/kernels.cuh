@@ -41,9 +41,15 @@ struct Counters {
 struct Outputs {
     uint32_t* rgba8;                    // raster [height][width] (world==1 or peer-memory target); else tile-compact [nlocal][8][32]
     int raster;                         // 1: rgba8 is a raster frame
-    float4* hitq;                       // hit queue: hitPos.xyz, w = colour(24) | normal(4)<<24
-    uint32_t* hitpix;                   // raster pixel id of each queue entry
+    float4* hitq;                       // per local tile, 256 slots: hitPos.xyz, w = colour(24) | normal(4)<<24 of the tile's hit pixels, compacted
+    uint32_t* hitpix;                   // raster pixel id of each entry
+    uint32_t* tile_hits;                // per local tile: number of entries
+    const uint32_t* shade_order;        // optional: launch order of the shade units (a unit = one shade block's share of a tile)
+    uint32_t* shade_cost;               // optional: per shade unit, SM cycles its block took this frame
+    int shade_unit_base;                // first shade unit of this launch
     Counters* counters;
+    const uint32_t* tile_order;         // optional: launch order of the local tiles (longest first, from the previous frame)
+    uint32_t* tile_cost;                // optional: per local tile, SM cycles its block took this frame
     int32_t* dbg_hit;                   // optional (VXRT_FLAG_DEBUG_OUTPUTS), raster layout
     uint16_t* dbg_steps;
     uint32_t* dbg_occl;
@@ -64,11 +70,14 @@ template <bool COUNT, class Grid>
 __global__ void __launch_bounds__(256, 6) primary_kernel(Grid g, const __grid_constant__ FrameParams f,
                                                       TileMap m, Outputs o) {
     __shared__ unsigned int s_warp_hits[8];
-    __shared__ unsigned int s_base;
     __shared__ unsigned long long s_fetches;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) s_fetches = 0ull;
-    const int t = (blockIdx.x + m.tile_base) * m.world + m.rank;    // global tile
+    const long long t_start = clock64();
+    // blocks are handed out in launch order: with a tile order from the previous frame the slowest tiles start first,
+    // which shortens the kernel's tail (it matters once a GPU renders only 1/4 or 1/8 of the frame)
+    const int local_tile = o.tile_order ? (int)o.tile_order[blockIdx.x] : (int)blockIdx.x + m.tile_base;
+    const int t = local_tile * m.world + m.rank;                    // global tile
     const int lx = (warp & 3) * 8 + (lane & 7), ly = (warp >> 2) * 4 + (lane >> 3);
     const int px = (t % m.tx) * TILE_W + lx, py = (t / m.tx) * TILE_H + ly;
     const bool valid = (t < m.ntiles) && (px < m.width) && (py < m.height);
@@ -102,7 +111,8 @@ __global__ void __launch_bounds__(256, 6) primary_kernel(Grid g, const __grid_co
             if (!hit) { o.dbg_occl[pid] = 0u; o.dbg_cast[pid] = 0u; }
         }
     }
-    // ---- hit compaction: warp ballot -> block prefix -> one global atomic per block -----------
+    // ---- hit compaction into the tile's 256 slots: warp ballot -> block prefix (no global ordering: the shade pass
+    //      schedules tiles by its own cost feedback) ---------------------------------------------------------------
     const unsigned ballot = __ballot_sync(0xffffffffu, hit);
     const unsigned wfetch = __reduce_add_sync(0xffffffffu, (unsigned)r.steps);
     if (lane == 0) s_warp_hits[warp] = __popc(ballot);
@@ -112,18 +122,68 @@ __global__ void __launch_bounds__(256, 6) primary_kernel(Grid g, const __grid_co
         unsigned total = 0;
         #pragma unroll
         for (int w = 0; w < 8; w++) { const unsigned c = s_warp_hits[w]; s_warp_hits[w] = total; total += c; }
-        s_base = total ? atomicAdd(&o.counters->hit_count, total) : 0u;
+        o.tile_hits[local_tile] = total;
+        if (total) atomicAdd(&o.counters->hit_count, total);          // statistics only
     }
     __syncthreads();
     if (hit) {
-        const unsigned pos = s_base + s_warp_hits[warp] + __popc(ballot & ((1u << lane) - 1u));
+        const unsigned pos = (unsigned)local_tile * TILE_PIX + s_warp_hits[warp] + __popc(ballot & ((1u << lane) - 1u));
         o.hitq[pos] = make_float4(r.hx, r.hy, r.hz, __uint_as_float(((uint32_t)r.voxel & 0x00FFFFFFu) | ((uint32_t)r.normal << 24)));
         o.hitpix[pos] = (uint32_t)(py * m.width + px);
     }
     if (tid == 0 && s_fetches) atomicAdd(&o.counters->fetches_primary, s_fetches);
+    if (tid == 0 && o.tile_cost) o.tile_cost[local_tile] = (uint32_t)min((long long)0xffffffffll, clock64() - t_start);
 }
 
-// ------------------------------------------------------------------------------------------------
+// cost[n] -> order[n], most expensive first: one-block counting sort on a 128-bucket logarithmic key.  Per-warp
+// private histograms and match_any ranking keep it free of contended atomics (costs cluster in a few buckets).
+__global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __restrict__ cost, uint32_t* __restrict__ order, int n) {
+    __shared__ unsigned int s_hist[32][128];                        // [warp][bucket] counts, then start positions
+    __shared__ unsigned int s_total[128];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 32 * 128; i += 1024) (&s_hist[0][0])[i] = 0u;
+    __syncthreads();
+    auto key = [](uint32_t c) -> int {                               // 127 = most expensive
+        if (c < 4u) return 0;
+        const int e = 31 - __clz(c);
+        const int k = e * 4 + (int)((c >> (e - 2)) & 3u);
+        return k > 127 ? 127 : k;
+    };
+    const int per_warp = (n + 31) / 32, w0 = min(n, warp * per_warp), w1 = min(n, w0 + per_warp);
+    for (int base = w0; base < w1; base += 32) {
+        const int i = base + lane;
+        const bool in = i < w1;
+        const int k = in ? key(cost[i]) : 128 + lane;                // out-of-range lanes get unique keys
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        if (in && lane == __ffs(peers) - 1) s_hist[warp][k] += __popc(peers);
+    }
+    __syncthreads();
+    if (tid < 128) {                                                 // per bucket: per-warp offsets inside the bucket, bucket total
+        unsigned acc = 0;
+        for (int w = 0; w < 32; w++) { const unsigned c = s_hist[w][tid]; s_hist[w][tid] = acc; acc += c; }
+        s_total[tid] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {                                                  // bucket start positions, most expensive bucket first
+        unsigned acc = 0;
+        for (int b = 127; b >= 0; b--) { const unsigned c = s_total[b]; s_total[b] = acc; acc += c; }
+    }
+    __syncthreads();
+    for (int base = w0; base < w1; base += 32) {
+        const int i = base + lane;
+        const bool in = i < w1;
+        const int k = in ? key(cost[i]) : 128 + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        if (in) {
+            const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+            order[s_total[k] + s_hist[warp][k] + rank] = (uint32_t)i;
+        }
+        __syncwarp();
+        if (in && lane == __ffs(peers) - 1) s_hist[warp][k] += __popc(peers);
+        __syncwarp();
+    }
+}
+
 template <bool COUNT, class Grid>
 __global__ void __launch_bounds__(256) shade_kernel(Grid g, const __grid_constant__ FrameParams f,
                                                     TileMap m, Outputs o) {
@@ -132,6 +192,16 @@ __global__ void __launch_bounds__(256) shade_kernel(Grid g, const __grid_constan
     __shared__ int s_nactive;
     __shared__ unsigned long long s_fetches, s_local;
     const int tid = threadIdx.x, lane = tid & 31;
+    // a shade unit = blockDim.x consecutive slots of one tile; units are launched slowest-first (previous frame's times)
+    const long long t_start = clock64();
+    const int unit = o.shade_order ? (int)o.shade_order[blockIdx.x] : (int)blockIdx.x + o.shade_unit_base;
+    const int units_per_tile = TILE_PIX / (int)blockDim.x;
+    const int tile = unit / units_per_tile, slot0 = (unit % units_per_tile) * (int)blockDim.x, slot = slot0 + tid;
+    const unsigned count = o.tile_hits[tile];
+    if ((unsigned)slot0 >= count) {                                  // sky tile / empty part of a tile: nothing to shade
+        if (tid == 0 && o.shade_cost) o.shade_cost[unit] = 0u;
+        return;
+    }
     if (tid < 32) {
         // fshader.glsl:167: a slot is in the scene iff x,y,z >= 0
         const bool act = (tid < 16) && f.lights[tid & 15][0] >= 0.0f && f.lights[tid & 15][1] >= 0.0f && f.lights[tid & 15][2] >= 0.0f;
@@ -144,10 +214,9 @@ __global__ void __launch_bounds__(256) shade_kernel(Grid g, const __grid_constan
         if (tid == 0) { s_nactive = __popc(b); s_fetches = 0ull; s_local = 0ull; }
     }
     __syncthreads();
-    const unsigned count = o.counters->hit_count;
-    const unsigned i = blockIdx.x * blockDim.x + tid;
+    const unsigned i = (unsigned)tile * TILE_PIX + (unsigned)slot;
     unsigned fetches = 0, nlocal = 0;
-    if (i < count) {
+    if ((unsigned)slot < count) {
         const float4 rec = o.hitq[i];
         const uint32_t pid = o.hitpix[i];
         const uint32_t packed = __float_as_uint(rec.w);
@@ -205,6 +274,7 @@ __global__ void __launch_bounds__(256) shade_kernel(Grid g, const __grid_constan
     if (lane == 0 && wf) { atomicAdd(&s_fetches, (unsigned long long)wf); atomicAdd(&s_local, (unsigned long long)wl); }
     __syncthreads();
     if (tid == 0 && s_fetches) { atomicAdd(&o.counters->fetches_shadow, s_fetches); atomicAdd(&o.counters->rays_local, s_local); }
+    if (tid == 0 && o.shade_cost) o.shade_cost[unit] = (uint32_t)min((long long)0xffffffffll, clock64() - t_start);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -55,6 +56,16 @@ struct vxrt_ctx {
     float4* d_hitq = nullptr;
     uint32_t* d_hitpix = nullptr;
     Counters* d_counters = nullptr;
+    uint32_t* d_tile_cost = nullptr;    // per local tile: block cycles of the last primary pass
+    uint32_t* d_tile_order = nullptr;   // launch order derived from it (longest first)
+    uint32_t* d_tile_hits = nullptr;    // per local tile: hit pixels queued for the shade pass
+    uint32_t* d_shade_cost = nullptr;   // per shade unit: block cycles of the last shade pass
+    uint32_t* d_shade_order = nullptr;
+    bool have_tile_order = false, have_shade_order = false;
+    int order_shade_threads = 0;        // block size the shade order was recorded with
+    unsigned long long order_frame = 0; // whole-frame launches since the ordering was (re)started
+    bool use_tile_order = true;
+    int shade_threads = 256;            // threads per shade block (VXRT_SHADE_THREADS: 64 / 128 / 256)
     int32_t* d_dbg_hit = nullptr;
     uint16_t* d_dbg_steps = nullptr;
     uint32_t* d_dbg_occl = nullptr;
@@ -100,6 +111,9 @@ static GridView grid_view(const vxrt_ctx* c) {
 
 static void free_frame_buffers(vxrt_ctx* c) {
     cudaFree(c->d_rgba8); cudaFree(c->d_rgba8_alt); cudaFree(c->d_hitq); cudaFree(c->d_hitpix);
+    cudaFree(c->d_tile_cost); cudaFree(c->d_tile_order); cudaFree(c->d_tile_hits); cudaFree(c->d_shade_cost); cudaFree(c->d_shade_order);
+    c->d_tile_cost = nullptr; c->d_tile_order = nullptr; c->d_tile_hits = nullptr; c->d_shade_cost = nullptr; c->d_shade_order = nullptr;
+    c->have_tile_order = false; c->have_shade_order = false; c->order_frame = 0;
     c->d_rgba8_alt = nullptr; c->slot_busy[0] = c->slot_busy[1] = false;
     cudaFree(c->d_dbg_hit); cudaFree(c->d_dbg_steps); cudaFree(c->d_dbg_occl); cudaFree(c->d_dbg_cast);
     c->d_rgba8 = nullptr; c->d_hitq = nullptr; c->d_hitpix = nullptr;
@@ -118,6 +132,14 @@ static int alloc_frame_buffers(vxrt_ctx* c) {
     CUDA_TRY(cudaMemsetAsync(c->d_rgba8, 0, c->out_pixels * 4, c->stream));
     CUDA_TRY(cudaMalloc(&c->d_hitq, local_pix * sizeof(float4)));
     CUDA_TRY(cudaMalloc(&c->d_hitpix, local_pix * 4));
+    CUDA_TRY(cudaMalloc(&c->d_tile_cost, (size_t)c->map.nlocal * 4));
+    CUDA_TRY(cudaMalloc(&c->d_tile_order, (size_t)c->map.nlocal * 4));
+    CUDA_TRY(cudaMalloc(&c->d_tile_hits, (size_t)c->map.nlocal * 4));
+    CUDA_TRY(cudaMalloc(&c->d_shade_cost, (size_t)c->map.nlocal * 4 * 4));      // up to 4 units per tile (64-thread blocks)
+    CUDA_TRY(cudaMalloc(&c->d_shade_order, (size_t)c->map.nlocal * 4 * 4));
+    CUDA_TRY(cudaMemsetAsync(c->d_tile_hits, 0, (size_t)c->map.nlocal * 4, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d_shade_cost, 0, (size_t)c->map.nlocal * 4 * 4, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d_tile_cost, 0, (size_t)c->map.nlocal * 4, c->stream));
     if (c->cfg.flags & VXRT_FLAG_DEBUG_OUTPUTS) {
         CUDA_TRY(cudaMalloc(&c->d_dbg_hit, npix * 4));
         CUDA_TRY(cudaMalloc(&c->d_dbg_steps, npix * 2));
@@ -258,6 +280,10 @@ extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     c->frame.aspect = (float)cfg->width / cfg->height;
     for (int i = 0; i < 4; i++) c->frame.rotate[5 * i] = 1.0f;
     vxrt_init_local_lights(c);
+    if (const char* e = getenv("VXRT_SHADE_THREADS")) {
+        const int v = atoi(e);
+        if (v == 64 || v == 128 || v == 256) c->shade_threads = v;
+    }
     *out = c;
     return VXRT_OK;
 }
@@ -537,8 +563,16 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         Outputs o;
         o.rgba8 = c->p2p ? (uint32_t*)(c->p2p_base + sizeof(P2PShared) + (c->p2p_seq & 1) * c->p2p_frame_bytes) : dev_out;
         o.raster = (c->cfg.world == 1 || c->p2p) ? 1 : 0;
-        o.hitq = c->d_hitq + (size_t)tile0 * TILE_PIX; o.hitpix = c->d_hitpix + (size_t)tile0 * TILE_PIX;
+        o.hitq = c->d_hitq; o.hitpix = c->d_hitpix; o.tile_hits = c->d_tile_hits;
         o.counters = c->d_counters + b;
+        // longest-tile-first launch order (whole-frame launches only; bands keep their contiguous tile ranges)
+        o.tile_order = (nbands == 1 && c->use_tile_order && c->have_tile_order) ? c->d_tile_order : nullptr;
+        o.tile_cost = (nbands == 1 && c->use_tile_order) ? c->d_tile_cost : nullptr;
+        const int upt = TILE_PIX / c->shade_threads;                  // shade units per tile
+        if (c->order_shade_threads != c->shade_threads) c->have_shade_order = false;
+        o.shade_order = (nbands == 1 && c->use_tile_order && c->have_shade_order) ? c->d_shade_order : nullptr;
+        o.shade_cost = (nbands == 1 && c->use_tile_order) ? c->d_shade_cost : nullptr;
+        o.shade_unit_base = tile0 * upt;
         o.dbg_hit = c->d_dbg_hit; o.dbg_steps = c->d_dbg_steps; o.dbg_occl = c->d_dbg_occl; o.dbg_cast = c->d_dbg_cast;
         const dim3 grid(ntile), block(256);
         if (ref_dims) {
@@ -551,16 +585,33 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         CUDA_TRY(cudaGetLastError());
         c->launches++;
         if (nbands == 1) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        // the launch orders are refreshed on the first two frames and then every 8th (block times are temporally
+        // coherent; the one-block sort costs ~30 us at 4K)
+        const bool refresh_order = c->order_frame < 2 || (c->order_frame % 8) == 0;
+        if (o.tile_cost && c->map.nlocal >= 64 && refresh_order) {
+            tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_tile_cost, c->d_tile_order, c->map.nlocal);
+            CUDA_TRY(cudaGetLastError());
+            c->launches++;
+            c->have_tile_order = true;
+        }
         if (c->frame.view_depth_field != 1) {
+            const dim3 sblock(c->shade_threads), sgrid((unsigned)(((size_t)ntile * TILE_PIX + c->shade_threads - 1) / c->shade_threads));
             if (ref_dims) {
-                if (count) shade_kernel<true, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, m, o);
-                else shade_kernel<false, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, m, o);
+                if (count) shade_kernel<true, GridViewRef><<<sgrid, sblock, 0, c->stream>>>(gr, fp, m, o);
+                else shade_kernel<false, GridViewRef><<<sgrid, sblock, 0, c->stream>>>(gr, fp, m, o);
             } else {
-                if (count) shade_kernel<true, GridView><<<grid, block, 0, c->stream>>>(g, fp, m, o);
-                else shade_kernel<false, GridView><<<grid, block, 0, c->stream>>>(g, fp, m, o);
+                if (count) shade_kernel<true, GridView><<<sgrid, sblock, 0, c->stream>>>(g, fp, m, o);
+                else shade_kernel<false, GridView><<<sgrid, sblock, 0, c->stream>>>(g, fp, m, o);
             }
             CUDA_TRY(cudaGetLastError());
             c->launches++;
+            if (o.shade_cost && c->map.nlocal >= 64 && refresh_order) {
+                tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_shade_cost, c->d_shade_order, c->map.nlocal * upt);
+                CUDA_TRY(cudaGetLastError());
+                c->launches++;
+                c->have_shade_order = true;
+                c->order_shade_threads = c->shade_threads;
+            }
         }
         if (host_dst) {
             size_t off, bytes;
@@ -577,6 +628,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
     }
     if (nbands != 1) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    if (nbands == 1 && c->use_tile_order) c->order_frame++;
     if (c->p2p) {
         p2p_signal_done_kernel<<<1, 1, 0, c->stream>>>((P2PShared*)c->p2p_base, c->cfg.rank, c->p2p_seq);
         CUDA_TRY(cudaGetLastError());
@@ -600,6 +652,14 @@ extern "C" int vxrt_set_readback_bands(vxrt_ctx* c, int nbands) {
     if (!c) return fail(VXRT_ERR_INVALID, "null context");
     if (nbands < 1 || nbands > MAX_BANDS) return fail(VXRT_ERR_INVALID, "readback bands must be in [1,16]");
     c->readback_bands = nbands;
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_set_tile_ordering(vxrt_ctx* c, int enabled) {
+    if (!c) return fail(VXRT_ERR_INVALID, "null context");
+    c->use_tile_order = enabled != 0;
+    if (!enabled) { c->have_tile_order = false; c->have_shade_order = false; }
+    c->order_frame = 0;
     return VXRT_OK;
 }
 
@@ -865,6 +925,29 @@ extern "C" int vxrt_p2p_release_frame(vxrt_ctx* c) {
     if (!c->p2p || !c->p2p_owner) return fail(VXRT_ERR_STATE, "p2p_release_frame: not the owner of a peer-memory target");
     if (c->p2p_seq == 0) return fail(VXRT_ERR_STATE, "p2p_release_frame before render");
     p2p_release_kernel<<<1, 1, 0, c->stream>>>((P2PShared*)c->p2p_base, c->p2p_seq - 1);
+    CUDA_TRY(cudaGetLastError());
+    return VXRT_OK;
+}
+
+// owner: queue "acquire every rank's flag -> copy the frame to page-locked host memory -> release the buffer" on the
+// copy stream and return; the main stream is free to start the next frame (double-buffered target)
+extern "C" int vxrt_p2p_readback(vxrt_ctx* c, uint8_t* out) {
+    CHECK_CTX(c);
+    if (!c->p2p || !c->p2p_owner) return fail(VXRT_ERR_STATE, "p2p_readback: not the owner of a peer-memory target");
+    if (c->p2p_seq == 0) return fail(VXRT_ERR_STATE, "p2p_readback before render");
+    if (!out) return fail(VXRT_ERR_INVALID, "p2p_readback: null output");
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned) return fail(VXRT_ERR_INVALID, "p2p_readback needs a page-locked destination (vxrt_host_alloc)");
+    const unsigned long long seq = c->p2p_seq - 1;
+    CUDA_TRY(cudaEventRecord(c->ev_band[0], c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_band[0], 0));
+    p2p_wait_done_kernel<<<1, 32, 0, c->copy_stream>>>((const P2PShared*)c->p2p_base, c->cfg.world, seq, c->d_p2p_err);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, c->p2p_base + sizeof(P2PShared) + (seq & 1) * c->p2p_frame_bytes, c->p2p_frame_bytes,
+                             cudaMemcpyDeviceToHost, c->copy_stream));
+    p2p_release_kernel<<<1, 1, 0, c->copy_stream>>>((P2PShared*)c->p2p_base, seq);
     CUDA_TRY(cudaGetLastError());
     return VXRT_OK;
 }
