@@ -54,6 +54,7 @@ def parse():
                     help="N > 1: 'p2p' = kernels store straight into rank 0's frame over NVLink (no collective); "
                          "'nccl' = all-gather of tile buffers + un-tile kernel")
     ap.add_argument("--bands", type=int, default=2, help="read-back bands of vxrt_render_frame_host (e2e, N = 1)")
+    ap.add_argument("--no-cull", action="store_true", help="disable the occupancy-summary culling of certain misses (vxrt_set_culling)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads / cpu baseline (profiling runs)")
     return ap.parse_args()
 
@@ -181,6 +182,7 @@ def run_b200(args):
     edit_state = {"k": 0}
 
     ren.setReadbackBands(args.bands)
+    ren.setCulling(not args.no_cull)
     use_p2p = world > 1 and args.exchange == "p2p"
     stream = torch.cuda.ExternalStream(ren.stream_ptr(), device=torch.device("cuda", local_rank))
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
@@ -372,6 +374,29 @@ def run_b200(args):
         t = torch.tensor([e2e_s, e2e_sync_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s, e2e_sync_s = (float(x) for x in t.tolist())
+    # the same timed loop with the miss culling switched off, for transparency (every ray marches to its end)
+    nocull = None
+    if not args.no_cull and not args.no_extra:
+        ren.setCulling(False)
+        for _ in range(5):
+            flush_l2(); step_device()
+        barrier()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for k in range(args.steps):
+            flush_l2()
+            ev2[k][0].record(stream)
+            step_device()
+            ev2[k][1].record(stream)
+            if k % 8 == 7 or k == args.steps - 1:
+                ren.sync()
+        barrier()
+        t_nc = float(sum(a.elapsed_time(b) for a, b in ev2))
+        if world > 1:
+            t = torch.tensor([t_nc], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_nc = float(t.item())
+        nocull = {"ms_per_step": round(t_nc / args.steps, 4), "value": round(rays / (t_nc / args.steps * 1e-3) / 1e6, 2), "unit": "Mrays/s"}
+        ren.setCulling(True)
     e2e_value = rays / (e2e_s / args.steps) / 1e6
     clocks = sampler.stop()
     h2d = 360                                                     # the frame parameters (kernel arguments)
@@ -417,6 +442,8 @@ def run_b200(args):
                        "partition": "sort-first 32x8 tiles, tile t -> rank t %% %d, grid replicated; frame exchange: %s" % (
                            world, "none (1 GPU)" if world == 1 else ("kernels store into rank 0's frame over NVLink peer memory, release/acquire flags" if use_p2p
                                                                      else "NCCL all-gather of RGBA8 tiles + un-tile kernel")),
+                       "miss_culling": ("off" if args.no_cull else "on: a ray ends as a miss once its cell is beyond every grid row holding a solid voxel "
+                                        "(occupancy summary, first-hit voxel and pixels unchanged; ray counts are the reference's)"),
                        "l2": "flushed between timed frames (256 MiB write)", "timing": "CUDA events on the launching stream per frame, max over ranks"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
@@ -426,6 +453,7 @@ def run_b200(args):
             "gpu_launches": int(args.steps * (st["kernel_launches"] + ((2 if use_p2p else 1) if world > 1 else 0))),
             "roofline": roofline,
             "wall_s_timed_region": round(t_wall, 3),
+            "without_miss_culling": nocull,
         }
         if scene == "C5":
             result["config"]["edits"] = "one vxrt_edit_remove_sphere(r=7) per frame, centres from mt19937(12345); rays/fetches are those of the last frame"

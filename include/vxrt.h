@@ -135,6 +135,10 @@ int vxrt_resize(vxrt_ctx* ctx, int width, int height);
 /* glDrawArrays(GL_TRIANGLES,0,6) main.cpp:59: runs the per-pixel path for this context's tiles; asynchronous */
 int vxrt_render(vxrt_ctx* ctx);
 int vxrt_sync(vxrt_ctx* ctx);
+/* enabled (default): production frames (counters off, no debug planes, not the step-count view) end a ray as a miss
+   as soon as its cell lies beyond every grid row that holds a solid voxel, in its direction of travel -- the coarsest
+   level of an occupancy hierarchy; the first-hit voxel and every pixel are unchanged (see ray.cuh CULL). */
+int vxrt_set_culling(vxrt_ctx* ctx, int enabled);
 /* enabled (default): the primary pass records how long each tile's block took and the next frame launches the
    slowest tiles first (shorter kernel tail; it matters when a GPU renders only a fraction of the frame).  Same pixels. */
 int vxrt_set_tile_ordering(vxrt_ctx* ctx, int enabled);

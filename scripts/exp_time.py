@@ -13,11 +13,13 @@ import voxel_rt_b200 as vx        # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=30)
 ap.add_argument("--workloads", default="C3ii_4k,C3i_4k,C2_1080p")
+ap.add_argument("--no-cull", action="store_true")
 ap.add_argument("--e2e", action="store_true", help="also sweep the read-back band count of the end-to-end call")
 a = ap.parse_args()
 W0, H0 = 3840, 2160
 ren = vx.Renderer(grid=vx.scenes.DEFAULT_GRID, width=W0, height=H0)
 ren.initVoxels(); ren.buildDepthField()
+ren.setCulling(not a.no_cull)
 assert vx.scenes.fnv1a64(ren.downloadGrid()) == 0x4c58cc4001a22afa
 stream = torch.cuda.ExternalStream(ren.stream_ptr())
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

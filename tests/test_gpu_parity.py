@@ -191,6 +191,61 @@ def test_pipelined_frame_submission(vx, oracle, default_level):
         assert np.array_equal(r.renderFrameHost(to_vx_frame(vx, gc.frame_cases(W, H)["C1"])), bufs[4])
 
 
+def test_miss_culling_never_changes_a_frame(vx, oracle, default_level):
+    """production kernels end a ray as a miss once its cell is beyond every row that holds a solid voxel (ray.cuh CULL);
+    frames must equal the counted (uncullled) variants and the oracle for cameras above / inside / below the solid rows,
+    looking up and down, and the summary must follow uploads and voxel placement"""
+    import oracle_lib as ol
+    W, H = 192, 108
+    rs = np.random.RandomState(21)
+    level = default_level.copy()
+    with vx.Renderer(grid=gc.DIMS, width=W, height=H) as r:
+        r.updateGeometry(level)
+        poses = []
+        for k in range(10):
+            a, b = float(rs.uniform(-1.5, 1.5)), float(rs.uniform(-3.1, 3.1))
+            ca, sa, cb, sb = np.cos(a), np.sin(a), np.cos(b), np.sin(b)
+            rotx = np.array([[1, 0, 0, 0], [0, ca, sa, 0], [0, -sa, ca, 0], [0, 0, 0, 1]], np.float32)
+            roty = np.array([[cb, 0, -sb, 0], [0, 1, 0, 0], [sb, 0, cb, 0], [0, 0, 0, 1]], np.float32)
+            rot = (roty.T @ rotx.T).T.astype(np.float32)
+            cam = (float(rs.uniform(20, 490)), float(rs.choice([38.5, 45.0, 51.5, 52.5, 60.0, 94.0])), float(rs.uniform(20, 490)))
+            lights = [(cam[0] + float(rs.uniform(-40, 40)), float(rs.uniform(37, 70)), cam[2] + float(rs.uniform(-40, 40)), 0.6) for _ in range(6)]
+            poses.append(ol.make_frame(cam, rotate=rot.ravel(), aspect=np.float32(W) / np.float32(H), lights=lights,
+                                       light_pos=(float(rs.uniform(-500, 1000)), float(rs.uniform(-200, 1600)), float(rs.uniform(-500, 1000)))))
+
+        def check_all(lvl):
+            for fr in poses:
+                r.setStats(False)
+                got = r.renderFrameHost(to_vx_frame(vx, fr))
+                r.setStats(True)
+                counted = r.renderFrameHost(to_vx_frame(vx, fr))
+                assert np.array_equal(got, counted)
+                assert np.array_equal(got, oracle.render(lvl, gc.DIMS, fr, W, H)["rgba8"])
+        check_all(level)
+        # a solid voxel far above everything else must become visible (placeVoxel extends the summary) ...
+        cam = poses[0].cam_pos
+        for dy in (70, 90, 95):
+            x, z = int(cam[0]) + 3, int(cam[2]) + 3
+            r.placeVoxel(x, dy, z, 0xff00ff)
+            level[x + 512 * dy + 512 * 96 * z] = 0xff00ff
+        check_all(level)
+        # ... and so must solids that arrive through a partial upload
+        level[300 + 512 * 80 + 512 * 96 * 300: 300 + 512 * 80 + 512 * 96 * 300 + 40] = 0x00ffff
+        r.uploadRange(300 + 512 * 80 + 512 * 96 * 300, level[300 + 512 * 80 + 512 * 96 * 300: 300 + 512 * 80 + 512 * 96 * 300 + 40])
+        check_all(level)
+    # an all-empty grid and a grid whose only solids sit at the top
+    for fill_row in (None, 15):
+        dims = (32, 16, 32)
+        lvl = np.full(dims[0] * dims[1] * dims[2], -1, np.int32)
+        if fill_row is not None:
+            lvl.reshape(dims[2], dims[1], dims[0])[:, fill_row, :] = 0x808080
+        fr = ol.make_frame((16.0, 8.0, 16.0), rotate=gc.PITCHED_ROTATE, aspect=np.float32(W) / np.float32(H), light_pos=(16.0, 96.0, 16.0))
+        with vx.Renderer(grid=dims, width=W, height=H) as r2:
+            r2.updateGeometry(lvl)
+            r2.setStats(False)
+            assert np.array_equal(r2.renderFrameHost(to_vx_frame(vx, fr)), oracle.render(lvl, dims, fr, W, H)["rgba8"])
+
+
 def test_render_is_idempotent_and_view_toggle(vx, ren):
     W, H = 160, 90
     ren.reshape(W, H)

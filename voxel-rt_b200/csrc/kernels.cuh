@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256, 6) primary_kernel(Grid g, const __grid_co
         const float rx = __fadd_rn(__fadd_rn(__fmul_rn(M[0], dxn), __fmul_rn(M[4], dyn)), __fadd_rn(__fmul_rn(M[8], dzn), __fmul_rn(M[12], 0.0f)));
         const float ry = __fadd_rn(__fadd_rn(__fmul_rn(M[1], dxn), __fmul_rn(M[5], dyn)), __fadd_rn(__fmul_rn(M[9], dzn), __fmul_rn(M[13], 0.0f)));
         const float rz = __fadd_rn(__fadd_rn(__fmul_rn(M[2], dxn), __fmul_rn(M[6], dyn)), __fadd_rn(__fmul_rn(M[10], dzn), __fmul_rn(M[14], 0.0f)));
-        r = cast_ray<COUNT, false>(g, f.cam_pos[0], f.cam_pos[1], f.cam_pos[2], rx, ry, rz, VXRT_RENDER_DIST);   // :139
+        r = cast_ray<COUNT, false, true>(g, f.cam_pos[0], f.cam_pos[1], f.cam_pos[2], rx, ry, rz, VXRT_RENDER_DIST);   // :139
         const uint32_t pid = (uint32_t)(py * m.width + px);
         if (f.view_depth_field == 1) {                               // :143-145
             const float grey = __fdiv_rn((float)r.steps, 100.0f);
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(256) shade_kernel(Grid g, const __grid_constan
         float multiplier = VXRT_AMBIENT;                             // :149
         uint32_t occl = 0u, cast = 1u;
         {   // :154 global-light shadow ray
-            const RayHit s = cast_ray<COUNT, true>(g, __fadd_rn(hx, __fmul_rn(lx, 0.001f)), __fadd_rn(hy, __fmul_rn(ly, 0.001f)),
+            const RayHit s = cast_ray<COUNT, true, true>(g, __fadd_rn(hx, __fmul_rn(lx, 0.001f)), __fadd_rn(hy, __fmul_rn(ly, 0.001f)),
                                       __fadd_rn(hz, __fmul_rn(lz, 0.001f)), lx, ly, lz, VXRT_RENDER_DIST);
             fetches += (unsigned)s.steps;
             if (s.idx == -1) multiplier = __fadd_rn(multiplier, __fmul_rn(VXRT_DIFFUSE, max0(dot3(nx, ny, nz, lx, ly, lz))));   // :155
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) shade_kernel(Grid g, const __grid_constan
             if (lld <= (float)VXRT_LOCAL_LIGHT_DIST) {                                       // :171
                 normalize3_with_length(tx, ty, tz, lld);                                    // :173 (same dot, same sqrt as :168)
                 cast |= 2u << slot; nlocal++;
-                const RayHit s = cast_ray<COUNT, true>(g, __fadd_rn(hx, __fmul_rn(tx, 0.001f)), __fadd_rn(hy, __fmul_rn(ty, 0.001f)),
+                const RayHit s = cast_ray<COUNT, true, false>(g, __fadd_rn(hx, __fmul_rn(tx, 0.001f)), __fadd_rn(hy, __fmul_rn(ty, 0.001f)),
                                           __fadd_rn(hz, __fmul_rn(tz, 0.001f)), tx, ty, tz, f2i(__fadd_rn(lld, 1.0f)));   // :175
                 fetches += (unsigned)s.steps;
                 if (s.idx == -1) {                                                          // :177
@@ -329,6 +329,24 @@ __global__ void carve_kernel(int32_t* __restrict__ vox, int w, int h, int d, Edi
     if (rx * rx + ry * ry + rz * rz < b.r2) vox[x + w * y + w * h * z] = -1;
 }
 
+// rows y that hold a solid voxel, over the linear range [first, first+count): block min/max -> atomics on out[0..1]
+__global__ void __launch_bounds__(256) yrange_kernel(const int32_t* __restrict__ vox, long long first, long long count, int w, int h,
+                                                     int* __restrict__ out) {
+    int lo = INT_MAX, hi = INT_MIN;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        if (vox[first + i] >= 0) {
+            const int y = (int)(((first + i) / w) % h);
+            lo = min(lo, y); hi = max(hi, y);
+        }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) {
+        if (lo != INT_MAX) atomicMin(&out[0], lo);
+        if (hi != INT_MIN) atomicMax(&out[1], hi);
+    }
+}
+
 __global__ void set_voxel_kernel(int32_t* vox, long long index, int32_t v) { vox[index] = v; }
 
 // one block per uploaded row: staging holds the rows back to back
@@ -344,8 +362,8 @@ __global__ void cast_rays_kernel(GridView g, int n, const float* __restrict__ st
                                  const int32_t* __restrict__ dists, int32_t* __restrict__ ret, float* __restrict__ out7) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const RayHit r = (i & 1) ? cast_ray<true, true>(g, starts[3 * i], starts[3 * i + 1], starts[3 * i + 2], dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], dists[i])
-                             : cast_ray<true, false>(g, starts[3 * i], starts[3 * i + 1], starts[3 * i + 2], dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], dists[i]);
+    const RayHit r = (i & 1) ? cast_ray<true, true, false>(g, starts[3 * i], starts[3 * i + 1], starts[3 * i + 2], dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], dists[i])
+                             : cast_ray<true, false, false>(g, starts[3 * i], starts[3 * i + 1], starts[3 * i + 2], dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], dists[i]);
     ret[i] = r.idx;
     float nx, ny, nz;
     unpack_normal(r.normal, nx, ny, nz);

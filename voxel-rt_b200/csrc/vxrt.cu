@@ -5,6 +5,8 @@
 #include "kernels.cuh"
 
 #include <cuda_runtime.h>
+#include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -47,6 +49,8 @@ struct vxrt_ctx {
     int32_t* d_vox = nullptr;
     size_t nvox = 0;
     bool grid_loaded = false;
+    int yrange[2] = {INT_MAX, INT_MIN};  // rows holding solid voxels (never shrinks on destruction: conservative)
+    int* d_yrange = nullptr;
     // frame state
     vxrt_frame frame{};
     TileMap map{};
@@ -65,6 +69,7 @@ struct vxrt_ctx {
     int order_shade_threads = 0;        // block size the shade order was recorded with
     unsigned long long order_frame = 0; // whole-frame launches since the ordering was (re)started
     bool use_tile_order = true;
+    bool use_culling = true;
     int shade_threads = 256;            // threads per shade block (VXRT_SHADE_THREADS: 64 / 128 / 256)
     int32_t* d_dbg_hit = nullptr;
     uint16_t* d_dbg_steps = nullptr;
@@ -106,6 +111,8 @@ static GridView grid_view(const vxrt_ctx* c) {
     GridView g;
     g.vox = c->d_vox; g.w = c->cfg.grid_w; g.h = c->cfg.grid_h; g.d = c->cfg.grid_d;
     g.wh = g.w * g.h; g.n = g.w * g.h * g.d;
+    g.ymin = c->yrange[0]; g.ymax = c->yrange[1];
+    if (!c->use_culling) { g.ymin = INT_MIN / 2; g.ymax = INT_MAX / 2; }      // "every row may hold a solid": nothing is ever culled
     return g;
 }
 
@@ -195,6 +202,22 @@ static int ensure_stage(vxrt_ctx* c, size_t elems, size_t rows) {
         CUDA_TRY(cudaMalloc(&c->d_first, cap * sizeof(long long)));
         c->first_cap = cap;
     }
+    return VXRT_OK;
+}
+
+// occupancy summary used by cast_ray's CULL: expand (or, reset = true, recompute) the range of rows with solid voxels
+// from the device grid's linear range [first, first+count)
+static int update_yrange(vxrt_ctx* c, size_t first, size_t count, bool reset) {
+    if (!c->d_yrange) CUDA_TRY(cudaMalloc(&c->d_yrange, 2 * sizeof(int)));
+    if (reset) { c->yrange[0] = INT_MAX; c->yrange[1] = INT_MIN; }
+    CUDA_TRY(cudaMemcpyAsync(c->d_yrange, c->yrange, 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (count) {
+        const unsigned blocks = (unsigned)std::min<size_t>((count + 255) / 256, 148 * 16);
+        yrange_kernel<<<blocks, 256, 0, c->stream>>>(c->d_vox, (long long)first, (long long)count, c->cfg.grid_w, c->cfg.grid_h, c->d_yrange);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->yrange, c->d_yrange, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     return VXRT_OK;
 }
 
@@ -295,6 +318,7 @@ extern "C" void vxrt_destroy(vxrt_ctx* c) {
     free_frame_buffers(c);
     if (c->p2p_base) { if (c->p2p_owner) cudaFree(c->p2p_base); else if (!c->p2p_attached) cudaIpcCloseMemHandle(c->p2p_base); }
     cudaFree(c->d_p2p_err);
+    cudaFree(c->d_yrange);
     cudaFree(c->d_vox); cudaFree(c->d_counters); cudaFree(c->d_stage); cudaFree(c->d_first);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_first) cudaFreeHost(c->h_first);
@@ -314,7 +338,7 @@ extern "C" int vxrt_upload_grid(vxrt_ctx* c, const int32_t* voxels, size_t count
     CUDA_TRY(cudaMemcpyAsync(c->d_vox, voxels, count * 4, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));      // GL semantics: the caller may modify its array on return
     c->grid_loaded = true;
-    return VXRT_OK;
+    return update_yrange(c, 0, c->nvox, true);
 }
 
 extern "C" int vxrt_upload_range(vxrt_ctx* c, size_t first, size_t count, const int32_t* src) {
@@ -323,7 +347,7 @@ extern "C" int vxrt_upload_range(vxrt_ctx* c, size_t first, size_t count, const 
     if (first > c->nvox || count > c->nvox - first) return fail(VXRT_ERR_INVALID, "upload_range: range outside the buffer (GL_INVALID_VALUE)");
     CUDA_TRY(cudaMemcpyAsync(c->d_vox + first, src, count * 4, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return VXRT_OK;
+    return update_yrange(c, first, count, false);
 }
 
 // updatePartialGeometry(start,end) render.cpp:204-223 -- same (int) casts, same float loop counters, same
@@ -357,6 +381,13 @@ extern "C" int vxrt_update_partial(vxrt_ctx* c, const float start_in[3], const f
     scatter_rows_kernel<<<(unsigned)rows, 64, 0, c->stream>>>(c->d_vox, c->d_stage, c->d_first, xLength);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(c->stream));      // staging buffers are reused by the next call
+    for (size_t r = 0; r < rows; r++)                 // rows uploaded may hold new solids
+        for (int i = 0; i < xLength; i++)
+            if (host_voxels[firsts[r] + i] >= 0) {
+                const int y = (int)(((firsts[r] + i) / c->cfg.grid_w) % c->cfg.grid_h);
+                if (y < c->yrange[0]) c->yrange[0] = y;
+                if (y > c->yrange[1]) c->yrange[1] = y;
+            }
     return VXRT_OK;
 }
 
@@ -391,7 +422,11 @@ extern "C" int vxrt_download_box(vxrt_ctx* c, const int32_t lo[3], const int32_t
 extern "C" int vxrt_place_voxel(vxrt_ctx* c, int x, int y, int z, int32_t voxel) {      // render.cpp:256-262
     CHECK_CTX(c);
     const int index = host_index(c->cfg, x, y, z);
-    if (index >= 0) { set_voxel_kernel<<<1, 1, 0, c->stream>>>(c->d_vox, index, voxel); CUDA_TRY(cudaGetLastError()); }
+    if (index >= 0) {
+        set_voxel_kernel<<<1, 1, 0, c->stream>>>(c->d_vox, index, voxel);
+        CUDA_TRY(cudaGetLastError());
+        if (voxel >= 0) { if (y < c->yrange[0]) c->yrange[0] = y; if (y > c->yrange[1]) c->yrange[1] = y; }
+    }
     return VXRT_OK;
 }
 
@@ -456,7 +491,7 @@ extern "C" int vxrt_generate_default_level(vxrt_ctx* c) {
     if (rc != VXRT_OK) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->grid_loaded = true;
-    return VXRT_OK;
+    return update_yrange(c, 0, c->nvox, true);
 }
 
 // config C4: integer fbm height field, the reference's material bands relative to the surface,
@@ -475,7 +510,7 @@ extern "C" int vxrt_generate_terrain(vxrt_ctx* c, uint64_t seed) {
     cudaFree(d_surface);
     if (rc != VXRT_OK) return rc;
     c->grid_loaded = true;
-    return VXRT_OK;
+    return update_yrange(c, 0, c->nvox, true);
 }
 
 extern "C" int vxrt_terrain_height(uint64_t seed, int x, int z, int grid_h) { return terrain_height(seed, x, z, grid_h); }
@@ -537,7 +572,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
     const bool count = c->count_stats || c->d_dbg_hit != nullptr;
     const bool count_primary = count || c->frame.view_depth_field == 1;
     const bool ref_dims = (g.w == GridViewRef::w && g.h == GridViewRef::h && g.d == GridViewRef::d);
-    GridViewRef gr; gr.vox = g.vox;
+    GridViewRef gr; gr.vox = g.vox; gr.ymin = g.ymin; gr.ymax = g.ymax;
     // bands: whole tile rows when this context owns the whole frame (raster rows stay contiguous), else tile ranges
     const int units = (c->cfg.world == 1) ? c->map.ty : c->map.nlocal;
     const int tiles_per_unit = (c->cfg.world == 1) ? c->map.tx : 1;
@@ -652,6 +687,12 @@ extern "C" int vxrt_set_readback_bands(vxrt_ctx* c, int nbands) {
     if (!c) return fail(VXRT_ERR_INVALID, "null context");
     if (nbands < 1 || nbands > MAX_BANDS) return fail(VXRT_ERR_INVALID, "readback bands must be in [1,16]");
     c->readback_bands = nbands;
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_set_culling(vxrt_ctx* c, int enabled) {
+    if (!c) return fail(VXRT_ERR_INVALID, "null context");
+    c->use_culling = enabled != 0;
     return VXRT_OK;
 }
 
