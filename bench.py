@@ -439,11 +439,13 @@ def run_b200(args):
                        "setup": build_info,
                        "view_depth_field": int(frame.view_depth_field), "rays_per_frame": rays, "rays_primary": rp, "rays_global": rg,
                        "rays_local": rl, "voxel_fetches_per_frame": fetches, "hit_pixels": hits,
+                       "rays_facing_away_from_their_light": int(st["rays_dark"]),
                        "partition": "sort-first 32x8 tiles, tile t -> rank t %% %d, grid replicated; frame exchange: %s" % (
                            world, "none (1 GPU)" if world == 1 else ("kernels store into rank 0's frame over NVLink peer memory, release/acquire flags" if use_p2p
                                                                      else "NCCL all-gather of RGBA8 tiles + un-tile kernel")),
-                       "miss_culling": ("off" if args.no_cull else "on: a ray ends as a miss once its cell is beyond every grid row holding a solid voxel "
-                                        "(occupancy summary, first-hit voxel and pixels unchanged; ray counts are the reference's)"),
+                       "miss_culling": ("off" if args.no_cull else "on: a ray ends as a miss once its cell is beyond every grid row holding a solid voxel (occupancy summary) and "
+                                        "rays from surfaces facing away from their light (term x max(0,N.L) = 0) are not traced; first-hit voxel and "
+                                        "pixels unchanged; ray counts are the reference's; 'without_miss_culling' is the same loop with both off"),
                        "l2": "flushed between timed frames (256 MiB write)", "timing": "CUDA events on the launching stream per frame, max over ranks"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_s / args.steps * 1e3, 4),

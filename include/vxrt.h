@@ -66,6 +66,8 @@ typedef struct {
     uint64_t rays_primary, rays_global, rays_local;
     uint64_t fetches;                /* castRay iterations == voxel fetches of the reference algorithm */
     uint64_t fetches_primary;        /* ... of which by primary rays (the rest: shadow / light rays) */
+    uint64_t rays_dark;              /* of rays_global + rays_local: rays toward a light the surface faces away from (N.L <= 0);
+                                        their outcome cannot change the pixel and production frames do not trace them */
     uint64_t hit_pixels;
     float ms_primary, ms_shadow, ms_total;   /* CUDA-event times of the last vxrt_render */
     uint32_t kernel_launches;        /* kernels launched by the last vxrt_render */
@@ -137,7 +139,9 @@ int vxrt_render(vxrt_ctx* ctx);
 int vxrt_sync(vxrt_ctx* ctx);
 /* enabled (default): production frames (counters off, no debug planes, not the step-count view) end a ray as a miss
    as soon as its cell lies beyond every grid row that holds a solid voxel, in its direction of travel -- the coarsest
-   level of an occupancy hierarchy; the first-hit voxel and every pixel are unchanged (see ray.cuh CULL). */
+   level of an occupancy hierarchy -- and do not trace shadow / light rays from surfaces that face away from the light
+   (their term is multiplied by max(0, N.L) = 0).  The first-hit voxel and every pixel are unchanged (ray.cuh CULL,
+   kernels.cuh skip_dark); ray statistics always count the rays the reference casts. */
 int vxrt_set_culling(vxrt_ctx* ctx, int enabled);
 /* enabled (default): the primary pass records how long each tile's block took and the next frame launches the
    slowest tiles first (shorter kernel tail; it matters when a GPU renders only a fraction of the frame).  Same pixels. */

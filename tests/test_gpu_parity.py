@@ -49,6 +49,7 @@ def check_frame(vx, oracle, ren, level, dims, fr, W, H):
     assert diff.max() <= RGB_TOL_LSB, "max RGBA8 difference %d LSB on %d pixels" % (diff.max(), int((diff.max(axis=2) > 0).sum()))
     c = ref["counters"]
     assert (st["rays_primary"], st["rays_global"], st["rays_local"], st["fetches"], st["hit_pixels"]) == tuple(int(x) for x in c)
+    assert 0 <= st["rays_dark"] <= st["rays_global"] + st["rays_local"]
     return rgba, dbg, st
 
 
@@ -221,6 +222,12 @@ def test_miss_culling_never_changes_a_frame(vx, oracle, default_level):
                 counted = r.renderFrameHost(to_vx_frame(vx, fr))
                 assert np.array_equal(got, counted)
                 assert np.array_equal(got, oracle.render(lvl, gc.DIMS, fr, W, H)["rgba8"])
+        check_all(level)
+        # light weights that are negative / infinite / NaN: the "term is zero" shortcut must not apply to non-finite ones
+        weird = ol.make_frame(gc.CAM, aspect=np.float32(W) / np.float32(H),
+                              lights=[(190.0, 40.0, 170.0, -0.5), (200.0, 45.0, 180.0, float("inf")), (185.0, 39.0, 165.0, float("nan")),
+                                      (205.0, 38.0, 160.0, 1e38), (195.0, 60.0, 175.0, 0.0)])
+        poses.append(weird)
         check_all(level)
         # a solid voxel far above everything else must become visible (placeVoxel extends the summary) ...
         cam = poses[0].cam_pos

@@ -36,7 +36,7 @@ class Frame(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("rays_primary", C.c_uint64), ("rays_global", C.c_uint64), ("rays_local", C.c_uint64),
-                ("fetches", C.c_uint64), ("fetches_primary", C.c_uint64), ("hit_pixels", C.c_uint64),
+                ("fetches", C.c_uint64), ("fetches_primary", C.c_uint64), ("rays_dark", C.c_uint64), ("hit_pixels", C.c_uint64),
                 ("ms_primary", C.c_float), ("ms_shadow", C.c_float), ("ms_total", C.c_float),
                 ("kernel_launches", C.c_uint32)]
 

@@ -36,11 +36,13 @@ struct Counters {
     unsigned int hit_count;
     unsigned int pad;
     unsigned long long rays_local, fetches_primary, fetches_shadow;
+    unsigned long long rays_dark;       // shadow / light rays whose surface faces away from the light (cannot change the pixel)
 };
 
 struct Outputs {
     uint32_t* rgba8;                    // raster [height][width] (world==1 or peer-memory target); else tile-compact [nlocal][8][32]
     int raster;                         // 1: rgba8 is a raster frame
+    int skip_dark;                      // production frames: do not trace rays whose outcome cannot change the pixel (N.L <= 0)
     float4* hitq;                       // per local tile, 256 slots: hitPos.xyz, w = colour(24) | normal(4)<<24 of the tile's hit pixels, compacted
     uint32_t* hitpix;                   // raster pixel id of each entry
     uint32_t* tile_hits;                // per local tile: number of entries
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(256) shade_kernel(Grid g, const __grid_constan
     }
     __syncthreads();
     const unsigned i = (unsigned)tile * TILE_PIX + (unsigned)slot;
-    unsigned fetches = 0, nlocal = 0;
+    unsigned fetches = 0, nlocal = 0, ndark = 0;
     if ((unsigned)slot < count) {
         const float4 rec = o.hitq[i];
         const uint32_t pid = o.hitpix[i];
@@ -223,12 +225,19 @@ __global__ void __launch_bounds__(256) shade_kernel(Grid g, const __grid_constan
         float nx, ny, nz;
         unpack_normal((int)(packed >> 24), nx, ny, nz);
         const float hx = rec.x, hy = rec.y, hz = rec.z;
+        // Rays toward a light the surface faces away from (N.L <= 0) add exactly +-0 to the multiplier whether they
+        // are occluded or not (fshader.glsl:155,177: "* max(0, dot(N, L))"), so production frames do not trace them; the
+        // sign test uses the unnormalised direction (normalising multiplies by a positive number).  Counted variants
+        // (statistics / debug planes) trace every ray the reference casts and report how many were of this kind.
+        const bool skip_dark = !COUNT && o.skip_dark != 0;
         // :147
         float lx = __fsub_rn(f.light_pos[0], hx), ly = __fsub_rn(f.light_pos[1], hy), lz = __fsub_rn(f.light_pos[2], hz);
-        normalize3(lx, ly, lz);
+        const bool g_lit = dot3(nx, ny, nz, lx, ly, lz) > 0.0f;
         float multiplier = VXRT_AMBIENT;                             // :149
         uint32_t occl = 0u, cast = 1u;
-        {   // :154 global-light shadow ray
+        if (COUNT && !g_lit) ndark++;
+        if (g_lit || !skip_dark) {   // :154 global-light shadow ray
+            normalize3(lx, ly, lz);
             const RayHit s = cast_ray<COUNT, true, true>(g, __fadd_rn(hx, __fmul_rn(lx, 0.001f)), __fadd_rn(hy, __fmul_rn(ly, 0.001f)),
                                       __fadd_rn(hz, __fmul_rn(lz, 0.001f)), lx, ly, lz, VXRT_RENDER_DIST);
             fetches += (unsigned)s.steps;
@@ -247,10 +256,14 @@ __global__ void __launch_bounds__(256) shade_kernel(Grid g, const __grid_constan
             const int slot = s_slot[k];
             last_slot = slot;
             float tx = __fsub_rn(L.x, hx), ty = __fsub_rn(L.y, hy), tz = __fsub_rn(L.z, hz);
+            // (a non-finite weight would turn the +-0 into NaN: such a light is always traced)
+            const bool lit = dot3(nx, ny, nz, tx, ty, tz) > 0.0f || !(fabsf(L.w) <= 3.0e38f);
+            if (skip_dark && !lit) continue;
             const float lld = __fsqrt_rn(dot3(tx, ty, tz, tx, ty, tz));                      // :168
             if (lld <= (float)VXRT_LOCAL_LIGHT_DIST) {                                       // :171
                 normalize3_with_length(tx, ty, tz, lld);                                    // :173 (same dot, same sqrt as :168)
                 cast |= 2u << slot; nlocal++;
+                if (COUNT && !lit) ndark++;
                 const RayHit s = cast_ray<COUNT, true, false>(g, __fadd_rn(hx, __fmul_rn(tx, 0.001f)), __fadd_rn(hy, __fmul_rn(ty, 0.001f)),
                                           __fadd_rn(hz, __fmul_rn(tz, 0.001f)), tx, ty, tz, f2i(__fadd_rn(lld, 1.0f)));   // :175
                 fetches += (unsigned)s.steps;
@@ -271,6 +284,10 @@ __global__ void __launch_bounds__(256) shade_kernel(Grid g, const __grid_constan
         if (o.dbg_occl) { o.dbg_occl[pid] = occl; o.dbg_cast[pid] = cast; }
     }
     const unsigned wf = __reduce_add_sync(0xffffffffu, fetches), wl = __reduce_add_sync(0xffffffffu, nlocal);
+    if (COUNT) {
+        const unsigned wd = __reduce_add_sync(0xffffffffu, ndark);
+        if (lane == 0 && wd) atomicAdd(&o.counters->rays_dark, (unsigned long long)wd);
+    }
     if (lane == 0 && wf) { atomicAdd(&s_fetches, (unsigned long long)wf); atomicAdd(&s_local, (unsigned long long)wl); }
     __syncthreads();
     if (tid == 0 && s_fetches) { atomicAdd(&o.counters->fetches_shadow, s_fetches); atomicAdd(&o.counters->rays_local, s_local); }

@@ -598,6 +598,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         Outputs o;
         o.rgba8 = c->p2p ? (uint32_t*)(c->p2p_base + sizeof(P2PShared) + (c->p2p_seq & 1) * c->p2p_frame_bytes) : dev_out;
         o.raster = (c->cfg.world == 1 || c->p2p) ? 1 : 0;
+        o.skip_dark = c->use_culling ? 1 : 0;
         o.hitq = c->d_hitq; o.hitpix = c->d_hitpix; o.tile_hits = c->d_tile_hits;
         o.counters = c->d_counters + b;
         // longest-tile-first launch order (whole-frame launches only; bands keep their contiguous tile ranges)
@@ -802,7 +803,7 @@ extern "C" int vxrt_get_stats(vxrt_ctx* c, vxrt_stats* out) {
     memset(&h, 0, sizeof h);
     for (int b = 0; b < MAX_BANDS; b++) {
         h.hit_count += hb[b].hit_count; h.rays_local += hb[b].rays_local;
-        h.fetches_primary += hb[b].fetches_primary; h.fetches_shadow += hb[b].fetches_shadow;
+        h.fetches_primary += hb[b].fetches_primary; h.fetches_shadow += hb[b].fetches_shadow; h.rays_dark += hb[b].rays_dark;
     }
     memset(out, 0, sizeof *out);
     // pixels this context rendered (padding tiles and clipped pixels excluded)
@@ -821,6 +822,7 @@ extern "C" int vxrt_get_stats(vxrt_ctx* c, vxrt_stats* out) {
     out->rays_local = h.rays_local;
     out->fetches = h.fetches_primary + h.fetches_shadow;
     out->fetches_primary = h.fetches_primary;
+    out->rays_dark = h.rays_dark;
     CUDA_TRY(cudaEventElapsedTime(&out->ms_primary, c->ev[0], c->ev[1]));
     CUDA_TRY(cudaEventElapsedTime(&out->ms_shadow, c->ev[1], c->ev[2]));
     CUDA_TRY(cudaEventElapsedTime(&out->ms_total, c->ev[0], c->ev[2]));
