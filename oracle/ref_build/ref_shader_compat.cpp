@@ -101,9 +101,13 @@ void ref_shader_pixel(int px, int py, int width, int height, float rgba[4], floa
 static int g_row_stride = 1;     // bounded samples: only 8-row blocks b with b % stride == 0 are rendered
 void ref_shader_set_row_stride(int s) { g_row_stride = s < 1 ? 1 : s; }
 
-static void render_rows(int width, int height, int y0, int y1, float* rgba, float* total_steps) {
+// rows [y0,y1) that pass the stride filter, dealt out 2 rows at a time to worker w of nw (nw = 1: all of them)
+static void render_rows(int width, int height, int y0, int y1, float* rgba, float* total_steps, int w = 0, int nw = 1) {
+    int selected = 0;
     for (int py = y0; py < y1; py++) {
         if (((py >> 3) % g_row_stride) != 0) continue;
+        const int mine = ((selected++ >> 1) % nw) == w;
+        if (!mine) continue;
         for (int px = 0; px < width; px++) {
             size_t p = (size_t)py * width + px;
             ref_shader_pixel(px, py, width, height, rgba + 4 * p, total_steps ? total_steps + p : nullptr);
@@ -120,15 +124,11 @@ int ref_shader_render(int width, int height, int y0, int y1, float* rgba, float*
     float* sh_rgba = (float*)mmap(nullptr, npix * 16, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
     float* sh_steps = (float*)mmap(nullptr, npix * 4, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
     if (sh_rgba == MAP_FAILED || sh_steps == MAP_FAILED) return -1;
-    const int block = 4;
     int failed = 0;
     for (int w = 0; w < nproc; w++) {
         pid_t pid = fork();
         if (pid == 0) {
-            for (int b = y0 + w * block; b < y1; b += nproc * block) {
-                int e = b + block < y1 ? b + block : y1;
-                render_rows(width, height, b, e, sh_rgba, sh_steps);
-            }
+            render_rows(width, height, y0, y1, sh_rgba, sh_steps, w, nproc);
             _exit(0);
         } else if (pid < 0) failed = 1;
     }
