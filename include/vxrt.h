@@ -137,6 +137,10 @@ int vxrt_resize(vxrt_ctx* ctx, int width, int height);
 /* glDrawArrays(GL_TRIANGLES,0,6) main.cpp:59: runs the per-pixel path for this context's tiles; asynchronous */
 int vxrt_render(vxrt_ctx* ctx);
 int vxrt_sync(vxrt_ctx* ctx);
+/* enabled: every frame starts with a prefetch sweep of the readable part of the grid into L2 (grids up to 120 MB).
+   Pays off when frames start with a cold L2 and a GPU renders only a fraction of the frame (the critical path of its
+   longest rays is otherwise a chain of HBM round trips); a few us of overhead when the L2 is warm anyway. */
+int vxrt_set_l2_prefetch(vxrt_ctx* ctx, int enabled);
 /* enabled (default): production frames (counters off, no debug planes, not the step-count view) end a ray as a miss
    as soon as its cell lies beyond every grid row that holds a solid voxel, in its direction of travel -- the coarsest
    level of an occupancy hierarchy -- and do not trace shadow / light rays from surfaces that face away from the light

@@ -14,10 +14,16 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=30)
 ap.add_argument("--workloads", default="C3ii_4k,C3i_4k,C2_1080p")
 ap.add_argument("--no-cull", action="store_true")
+ap.add_argument("--world", type=int, default=1, help="emulate one rank of an N-GPU split on this GPU (rank 0's tiles only)")
+ap.add_argument("--prefetch", type=int, default=0)
+ap.add_argument("--no-flush", action="store_true")
+ap.add_argument("--no-order", action="store_true")
 ap.add_argument("--e2e", action="store_true", help="also sweep the read-back band count of the end-to-end call")
 a = ap.parse_args()
 W0, H0 = 3840, 2160
-ren = vx.Renderer(grid=vx.scenes.DEFAULT_GRID, width=W0, height=H0)
+ren = vx.Renderer(grid=vx.scenes.DEFAULT_GRID, width=W0, height=H0, rank=0, world=a.world)
+ren.setL2Prefetch(a.prefetch)
+ren.setTileOrdering(not a.no_order)
 ren.initVoxels(); ren.buildDepthField()
 ren.setCulling(not a.no_cull)
 assert vx.scenes.fnv1a64(ren.downloadGrid()) == 0x4c58cc4001a22afa
@@ -36,8 +42,9 @@ for wl in a.workloads.split(","):
     ren.sync()
     p, s, t = [], [], []
     for _ in range(a.frames):
-        with torch.cuda.stream(stream):
-            flush.fill_(1)
+        if not a.no_flush:
+            with torch.cuda.stream(stream):
+                flush.fill_(1)
         ren.draw()
         x = ren.stats()
         p.append(x["ms_primary"]); s.append(x["ms_shadow"]); t.append(x["ms_total"])

@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 N=${1:-4}
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 scripts/multigpu_check.py 2>&1 | grep -v "^W\|^\[W" | tail -8
-for X in p2p nccl; do
+for X in ${EXCH:-p2p nccl}; do
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus $N --steps 30 --warmup 5 --exchange $X > gpurun_out/bench_mg${N}_$X.json 2> gpurun_out/bench_mg${N}_$X.err; python -c "
 import json,sys
 d=json.loads(open('gpurun_out/bench_mg${N}_$X.json').read().strip().splitlines()[-1])

@@ -73,6 +73,7 @@ _SIGNATURES = {
     "vxrt_render": (C.c_int, [C.c_void_p]),
     "vxrt_sync": (C.c_int, [C.c_void_p]),
     "vxrt_set_readback_bands": (C.c_int, [C.c_void_p, C.c_int]),
+    "vxrt_set_l2_prefetch": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_culling": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_tile_ordering": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
@@ -283,6 +284,9 @@ class Renderer:
     def draw(self):
         """glDrawArrays(GL_TRIANGLES,0,6) main.cpp:59 (asynchronous)."""
         self._check(self.lib.vxrt_render(self._h))
+
+    def setL2Prefetch(self, enabled):
+        self._check(self.lib.vxrt_set_l2_prefetch(self._h, 1 if enabled else 0))
 
     def setCulling(self, enabled):
         self._check(self.lib.vxrt_set_culling(self._h, 1 if enabled else 0))

@@ -346,6 +346,19 @@ __global__ void carve_kernel(int32_t* __restrict__ vox, int w, int h, int d, Edi
     if (rx * rx + ry * ry + rz * rz < b.r2) vox[x + w * y + w * h * z] = -1;
 }
 
+// Pull the part of the grid rays can read (rows 0 .. ytop-1 of every z slab) into L2 ahead of the traversal: a frame
+// that starts with a cold L2 otherwise pays an HBM round trip (~1 us) on the critical path of every long ray for each
+// new line it touches -- which is what bounds the frame once a GPU renders only 1/4 or 1/8 of it.  One prefetch per
+// 128-byte line; ~10 us for the reference level.
+__global__ void __launch_bounds__(256) l2_prefetch_kernel(const int32_t* __restrict__ vox, int lines_per_slab, int slab_stride_ints, long long nlines) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x; l < nlines; l += stride) {
+        const long long z = l / lines_per_slab, j = l - z * lines_per_slab;
+        const int32_t* p = vox + z * slab_stride_ints + j * 32;
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+    }
+}
+
 // rows y that hold a solid voxel, over the linear range [first, first+count): block min/max -> atomics on out[0..1]
 __global__ void __launch_bounds__(256) yrange_kernel(const int32_t* __restrict__ vox, long long first, long long count, int w, int h,
                                                      int* __restrict__ out) {
