@@ -137,10 +137,11 @@ int vxrt_resize(vxrt_ctx* ctx, int width, int height);
 /* glDrawArrays(GL_TRIANGLES,0,6) main.cpp:59: runs the per-pixel path for this context's tiles; asynchronous */
 int vxrt_render(vxrt_ctx* ctx);
 int vxrt_sync(vxrt_ctx* ctx);
-/* enabled: every frame starts with a prefetch sweep of the readable part of the grid into L2 (grids up to 120 MB).
-   Pays off when frames start with a cold L2 and a GPU renders only a fraction of the frame (the critical path of its
-   longest rays is otherwise a chain of HBM round trips); a few us of overhead when the L2 is warm anyway. */
-int vxrt_set_l2_prefetch(vxrt_ctx* ctx, int enabled);
+/* mode 1: every frame starts with a streaming read of the part of the grid rays can reach, which allocates it in L2
+   (grids up to 120 MB).  It pays off when frames start with a cold L2 and the context renders few pixels -- the
+   critical path of its longest rays is otherwise a chain of ~1 us HBM round trips -- and costs ~15 us otherwise.
+   mode 0: never; mode 2 (default): when this context renders at most 12,000 tiles (1080p, or a quarter of a 4K frame). */
+int vxrt_set_l2_prefetch(vxrt_ctx* ctx, int mode);
 /* enabled (default): production frames (counters off, no debug planes, not the step-count view) end a ray as a miss
    as soon as its cell lies beyond every grid row that holds a solid voxel, in its direction of travel -- the coarsest
    level of an occupancy hierarchy -- and do not trace shadow / light rays from surfaces that face away from the light

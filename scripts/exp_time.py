@@ -15,7 +15,7 @@ ap.add_argument("--frames", type=int, default=30)
 ap.add_argument("--workloads", default="C3ii_4k,C3i_4k,C2_1080p")
 ap.add_argument("--no-cull", action="store_true")
 ap.add_argument("--world", type=int, default=1, help="emulate one rank of an N-GPU split on this GPU (rank 0's tiles only)")
-ap.add_argument("--prefetch", type=int, default=0)
+ap.add_argument("--prefetch", type=int, default=2)
 ap.add_argument("--no-flush", action="store_true")
 ap.add_argument("--no-order", action="store_true")
 ap.add_argument("--e2e", action="store_true", help="also sweep the read-back band count of the end-to-end call")

@@ -256,6 +256,7 @@ def test_miss_culling_never_changes_a_frame(vx, oracle, default_level):
 def test_render_is_idempotent_and_view_toggle(vx, ren):
     W, H = 160, 90
     ren.reshape(W, H)
+    ren.setL2Prefetch(0)                                             # (its sweep kernel would add one launch per frame)
     fr = to_vx_frame(vx, gc.frame_cases(W, H)["C2"])
     a = ren.renderFrameHost(fr)
     b = ren.renderFrameHost(fr)
@@ -283,6 +284,10 @@ def test_render_is_idempotent_and_view_toggle(vx, ren):
         launches.append(ren.stats()["kernel_launches"])
         assert np.array_equal(ren.readPixels(), want)
     assert launches[0] == 4 and launches[1] == 4 and launches[2] == 2 and launches[8] == 4     # orders refreshed on frames 0, 1, 8, ...
+    ren.setL2Prefetch(1)                                             # the cold-L2 sweep: one more launch, same pixels
+    ren.draw()
+    assert ren.stats()["kernel_launches"] == 3 and np.array_equal(ren.readPixels(), want)
+    ren.setL2Prefetch(2)
 
 
 # ---- other grid shapes ---------------------------------------------------------------------------

@@ -285,8 +285,9 @@ class Renderer:
         """glDrawArrays(GL_TRIANGLES,0,6) main.cpp:59 (asynchronous)."""
         self._check(self.lib.vxrt_render(self._h))
 
-    def setL2Prefetch(self, enabled):
-        self._check(self.lib.vxrt_set_l2_prefetch(self._h, 1 if enabled else 0))
+    def setL2Prefetch(self, mode):
+        """0 off, 1 on, 2 auto (default)"""
+        self._check(self.lib.vxrt_set_l2_prefetch(self._h, int(mode)))
 
     def setCulling(self, enabled):
         self._check(self.lib.vxrt_set_culling(self._h, 1 if enabled else 0))

@@ -70,7 +70,7 @@ struct vxrt_ctx {
     unsigned long long order_frame = 0; // whole-frame launches since the ordering was (re)started
     bool use_tile_order = true;
     bool use_culling = true;
-    int l2_prefetch = 0;                // VXRT_L2_PREFETCH / vxrt_set_l2_prefetch: sweep the readable part of the grid into L2 before every frame
+    int l2_prefetch = 2;                // vxrt_set_l2_prefetch: 0 off, 1 on, 2 auto (on when this context renders <= 12,000 tiles)
     int shade_threads = 256;            // threads per shade block (VXRT_SHADE_THREADS: 64 / 128 / 256)
     int32_t* d_dbg_hit = nullptr;
     uint16_t* d_dbg_steps = nullptr;
@@ -304,7 +304,7 @@ extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     c->frame.aspect = (float)cfg->width / cfg->height;
     for (int i = 0; i < 4; i++) c->frame.rotate[5 * i] = 1.0f;
     vxrt_init_local_lights(c);
-    if (const char* e = getenv("VXRT_L2_PREFETCH")) c->l2_prefetch = atoi(e) != 0;
+    if (const char* e = getenv("VXRT_L2_PREFETCH")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->l2_prefetch = v; }
     if (const char* e = getenv("VXRT_SHADE_THREADS")) {
         const int v = atoi(e);
         if (v == 64 || v == 128 || v == 256) c->shade_threads = v;
@@ -591,14 +591,15 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         c->launches++;
     }
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    if (c->l2_prefetch && (size_t)c->nvox * 4 <= (size_t)120 << 20) {      // only grids that fit the 126 MB L2
+    const bool sweep = c->l2_prefetch == 1 || (c->l2_prefetch == 2 && c->map.nlocal <= 12000);
+    if (sweep && (size_t)c->nvox * 4 <= (size_t)120 << 20) {              // only grids that fit the 126 MB L2
         // rows a ray can read: up to 7 above the highest solid row (beyond that the culling ends the ray), all rows otherwise
         int ytop = c->cfg.grid_h;
         if (c->use_culling && !count && c->yrange[1] >= c->yrange[0]) ytop = std::min(c->cfg.grid_h, c->yrange[1] + 9);
         const int slab_ints = c->cfg.grid_w * c->cfg.grid_h;
         const int lines_per_slab = (c->cfg.grid_w * ytop + 31) / 32;
         const long long nlines = (long long)lines_per_slab * c->cfg.grid_d;
-        l2_prefetch_kernel<<<148 * 8, 256, 0, c->stream>>>(c->d_vox, lines_per_slab, slab_ints, nlines);
+        l2_prefetch_kernel<<<148 * 8, 256, 0, c->stream>>>(c->d_vox, lines_per_slab, slab_ints, nlines, (int*)&c->d_counters[MAX_BANDS - 1].pad);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
     }
@@ -706,7 +707,8 @@ extern "C" int vxrt_set_readback_bands(vxrt_ctx* c, int nbands) {
 
 extern "C" int vxrt_set_l2_prefetch(vxrt_ctx* c, int enabled) {
     if (!c) return fail(VXRT_ERR_INVALID, "null context");
-    c->l2_prefetch = enabled != 0;
+    if (enabled < 0 || enabled > 2) return fail(VXRT_ERR_INVALID, "l2_prefetch: 0 off, 1 on, 2 auto");
+    c->l2_prefetch = enabled;
     return VXRT_OK;
 }
 
