@@ -203,4 +203,43 @@ void ref_host_mouse_look_matrix(float rx, float ry, float* rot16, float* dir3) {
     dir3[0] = d.x; dir3[1] = d.y; dir3[2] = d.z;
 }
 
+// ---- gameplay (controls.cpp:10-98, 112-144) through the reference's own functions ----------------------------
+}  // extern "C"
+int collided();   // controls.cpp:10, external linkage but not in controls.hpp
+void initLocalLights();   // render.cpp:304, likewise
+extern "C" {
+// controls.cpp keeps `gravity` in a file-static; the only way to zero it is the reference's own "hit something"
+// branch of doGravity(): stand the camera in a temporarily solid voxel.
+void ref_host_reset_gravity(void) {
+    const glm::vec3 keep = camPos;
+    const int idx = getVoxelIndex(5, 5, 5), old = voxels[idx];
+    voxels[idx] = 0;
+    camPos = glm::vec3(5.5f, 11.5f, 5.5f);
+    doGravity();
+    voxels[idx] = old;
+    camPos = keep;
+}
+void ref_host_player_set(const float cam[3], const float dir[3], const float camrot[2], long long fps_) {
+    camPos = glm::vec3(cam[0], cam[1], cam[2]);
+    camDir = glm::vec3(dir[0], dir[1], dir[2]);
+    camRotation = glm::vec2(camrot[0], camrot[1]);
+    rotateMatrix = glm::mat4(1.0f);
+    viewDepthField = 0;
+    fps = fps_;
+    for (int k = 0; k < KEYS; k++) keys[k] = false;
+}
+void ref_host_player_keys(const unsigned char k9[9]) { for (int k = 0; k < KEYS; k++) keys[k] = k9[k] != 0; }
+void ref_host_player_mouse(int mx, int my, int sw, int sh) { mouseX = mx; mouseY = my; screenWidth = sw; screenHeight = sh; }
+// the host part of one main-loop iteration (main.cpp:62-65)
+void ref_host_player_step(void) { movementUpdate(); doMouseLook(); doGravity(); }
+int ref_host_player_get(float out24[24]) {
+    out24[0] = camPos.x; out24[1] = camPos.y; out24[2] = camPos.z;
+    out24[3] = camDir.x; out24[4] = camDir.y; out24[5] = camDir.z;
+    out24[6] = camRotation.x; out24[7] = camRotation.y;
+    memcpy(out24 + 8, glm::value_ptr(rotateMatrix), 64);
+    return viewDepthField;
+}
+void ref_host_init_lights(void) { initLocalLights(); }
+int ref_host_collided(const float cam[3]) { camPos = glm::vec3(cam[0], cam[1], cam[2]); return collided(); }
+
 }  // extern "C"

@@ -218,6 +218,64 @@ class RefHost:
         self.L.ref_host_mouse_look_matrix(C.c_float(rx), C.c_float(ry), _ptr(rot, C.c_float), _ptr(d, C.c_float))
         return rot, d
 
+    # ---- gameplay (controls.cpp) ----
+    def player_reset(self, cam, direction, camrot, fps):
+        self.L.ref_host_player_set((C.c_float * 3)(*cam), (C.c_float * 3)(*direction), (C.c_float * 2)(*camrot), C.c_longlong(fps))
+        self.L.ref_host_reset_gravity()
+        self.L.ref_host_init_lights()
+
+    def player_step(self, keys9, mouse):
+        """keys persist in the reference (T / SHIFT clear themselves), so the caller passes the full state each frame"""
+        self.L.ref_host_player_keys((C.c_ubyte * 9)(*keys9))
+        self.L.ref_host_player_mouse(*[C.c_int(int(v)) for v in mouse])
+        self.L.ref_host_player_step()
+        out = np.zeros(24, np.float32)
+        view = self.L.ref_host_player_get(_ptr(out, C.c_float))
+        return out, view
+
+    def collided(self, cam):
+        return self.L.ref_host_collided((C.c_float * 3)(*cam))
+
+
+class HostLogic:
+    """voxel-rt_b200/libvxrt_hostlogic.so: the product's host gameplay code (CPU only, no device calls)."""
+
+    def __init__(self, voxels, dims=(512, 96, 512)):
+        import importlib
+        build = importlib.import_module("voxel_rt_b200").build
+        L = self.L = C.CDLL(build.build_hostlogic())
+        L.vxh_player_create.restype = C.c_void_p
+        self.voxels = np.ascontiguousarray(voxels, np.int32)
+        self.p = C.c_void_p(L.vxh_player_create(_ptr(self.voxels, C.c_int32), *[C.c_int(v) for v in dims]))
+
+    def reset(self, cam, direction, camrot, fps):
+        self.L.vxh_player_set(self.p, (C.c_float * 3)(*cam), (C.c_float * 3)(*direction), (C.c_float * 2)(*camrot), C.c_longlong(fps))
+
+    def step(self, keys9, mouse):
+        self.L.vxh_player_keys(self.p, (C.c_ubyte * 9)(*keys9))
+        self.L.vxh_player_mouse(self.p, *[C.c_int(int(v)) for v in mouse])
+        self.L.vxh_player_step(self.p)
+        out = np.zeros(24, np.float32)
+        view = self.L.vxh_player_get(self.p, _ptr(out, C.c_float))
+        return out, view
+
+    def take_light(self):
+        out = np.zeros(3, np.float32)
+        return out if self.L.vxh_player_take_light(self.p, _ptr(out, C.c_float)) else None
+
+    def collided(self, cam):
+        return self.L.vxh_player_collided(self.p, (C.c_float * 3)(*cam))
+
+    def rotate(self, angle, axis):
+        out = np.zeros(16, np.float32)
+        self.L.vxh_mat4_rotate(C.c_float(angle), *[C.c_float(a) for a in axis], _ptr(out, C.c_float))
+        return out
+
+    def close(self):
+        if self.p:
+            self.L.vxh_player_destroy(self.p)
+            self.p = None
+
 
 class RefShader:
     """oracle/_ref/libref_shader.so: the reference's fshader.glsl compiled as C++ (512x96x512 only)."""

@@ -45,3 +45,35 @@ def test_headless_destroy_then_frame(vx, oracle, default_level, tmp_path):
     oracle.do_destroy(level, gc.DIMS, gc.CAM, (0.0, -1.0, 0.0))
     fr = ol.make_frame(gc.CAM, aspect=np.float32(W) / np.float32(H), view=1)
     assert np.array_equal(got, oracle.render(level, gc.DIMS, fr, W, H)["rgba8"])
+
+
+def test_headless_scripted_walk(vx, oracle, default_level, tmp_path):
+    """main.cpp:58-66 with scripted input: movementUpdate / doMouseLook / doGravity on the host mirror, a light dropped
+    half way (T), a dig on the last frame (RMB); final pose and frame against the host-logic library + oracle"""
+    W, H, N = 320, 180, 90
+    raw, _, log = run_headless(vx, tmp_path, "--size", W, H, "--walk", N)
+    line = [l for l in log.splitlines() if l.startswith("walk")][0].split()
+    pose = np.array([float.fromhex(v) for v in line[3:6] + line[7:10] + line[11:13]], np.float32)
+    hl = ol.HostLogic(default_level, gc.DIMS)
+    hl.reset(gc.CAM, (0.0, 0.0, 1.0), (0.0, 0.0), 60)
+    lights = []
+    for f in range(N):
+        keys = [0] * 9
+        keys[0] = keys[7] = 1
+        keys[5] = int(f % 45 == 0)
+        keys[4] = int(f == N // 2)
+        st, view = hl.step(keys, (W // 2 + W // 20, H // 2 + H // 60, W, H))
+        l = hl.take_light()
+        if l is not None:
+            lights.append(l)
+    hl.close()
+    assert np.array_equal(pose.view(np.uint32), st[:8].view(np.uint32))
+    assert len(lights) == 1
+    level = default_level.copy()
+    oracle.do_destroy(level, gc.DIMS, st[0:3], st[3:6])
+    lt = np.full((16, 4), -1.0, np.float32)
+    lt[:, 3] = 0.0
+    lt[0] = [lights[0][0], lights[0][1], lights[0][2], 0.5]
+    fr = ol.make_frame(st[0:3], rotate=st[8:24], aspect=np.float32(W) / np.float32(H), lights=lt, cam_rotation=(float(st[6]), float(st[7])))
+    got = np.fromfile(raw, np.uint8).reshape(H, W, 4)
+    assert np.array_equal(got, oracle.render(level, gc.DIMS, fr, W, H)["rgba8"])

@@ -18,8 +18,23 @@ NVCC_FLAGS = [
 ]
 
 
-HOST_SRCS = [os.path.join(HERE, "csrc", "host", "vxrt_render.cpp"), os.path.join(HERE, "csrc", "host", "vxrt_headless.cpp")]
-HOST_DEPS = HOST_SRCS + [os.path.join(HERE, "csrc", "host", "vxrt_render.hpp")]
+CONTROLS_SRC = os.path.join(HERE, "csrc", "host", "vxrt_controls.cpp")
+HOST_SRCS = [os.path.join(HERE, "csrc", "host", "vxrt_render.cpp"), os.path.join(HERE, "csrc", "host", "vxrt_headless.cpp"), CONTROLS_SRC]
+HOST_DEPS = HOST_SRCS + [os.path.join(HERE, "csrc", "host", "vxrt_render.hpp"), os.path.join(HERE, "csrc", "host", "vxrt_controls.hpp")]
+HOSTLOGIC = os.path.join(HERE, "libvxrt_hostlogic.so")
+
+
+def build_hostlogic(force=False):
+    """the host gameplay logic (controls.cpp restated) as a CPU-only shared library for the parity tests"""
+    deps = [CONTROLS_SRC, os.path.join(HERE, "csrc", "host", "vxrt_controls.hpp")]
+    if not force and os.path.exists(HOSTLOGIC) and all(os.path.getmtime(d) <= os.path.getmtime(HOSTLOGIC) for d in deps):
+        return HOSTLOGIC
+    cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-fPIC", "-shared", "-o", HOSTLOGIC, CONTROLS_SRC]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building libvxrt_hostlogic.so")
+    return HOSTLOGIC
 HEADLESS = os.path.join(HERE, "vxrt_headless")
 
 
@@ -27,7 +42,7 @@ def build_host(force=False):
     """the C++ host mirror of render.hpp + the headless game-loop driver, linked against libvxrt.so"""
     if not force and os.path.exists(HEADLESS) and all(os.path.getmtime(d) <= os.path.getmtime(HEADLESS) for d in HOST_DEPS + [LIB]):
         return HEADLESS
-    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", HEADLESS] + HOST_SRCS + ["-L" + HERE, "-lvxrt", "-Wl,-rpath,$ORIGIN"]
+    cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-o", HEADLESS] + HOST_SRCS + ["-L" + HERE, "-lvxrt", "-Wl,-rpath,$ORIGIN"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -66,3 +81,4 @@ def build(force=False, verbose=False):
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_host(force="--force" in sys.argv))
+    print(build_hostlogic(force="--force" in sys.argv))

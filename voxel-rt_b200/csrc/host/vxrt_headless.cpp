@@ -1,7 +1,7 @@
 // vxrt_headless.cpp -- the reference's game loop (src/main.cpp:47-75) run headless on the B200 path: no window,
 // frames go to PPM files / a raw RGBA8 dump instead of glfwSwapBuffers.  Used by tests/test_gpu_host.py.
 //
-//   vxrt_headless [--size W H] [--frames N] [--lights] [--pitched] [--view] [--destroy] [--ppm out.ppm] [--raw out.rgba]
+//   vxrt_headless [--size W H] [--frames N] [--lights] [--pitched] [--view] [--destroy] [--walk N] [--ppm out.ppm] [--raw out.rgba]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -13,7 +13,7 @@
 using namespace vxrt_host;
 
 int main(int argc, char** argv) {
-    int W = 1280, H = 720, frames = 1;
+    int W = 1280, H = 720, frames = 1, walk = 0;
     bool lights = false, pitched = false, view = false, destroy = false;
     std::string ppm, raw;
     for (int i = 1; i < argc; i++) {
@@ -24,6 +24,7 @@ int main(int argc, char** argv) {
         else if (a == "--pitched") pitched = true;
         else if (a == "--view") view = true;
         else if (a == "--destroy") destroy = true;
+        else if (a == "--walk" && i + 1 < argc) walk = atoi(argv[++i]);
         else if (a == "--ppm" && i + 1 < argc) ppm = argv[++i];
         else if (a == "--raw" && i + 1 < argc) raw = argv[++i];
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
@@ -39,6 +40,19 @@ int main(int argc, char** argv) {
             r.placeLocalLight(r.camPos.x - 36 + 24 * (i % 4), 40.0f, r.camPos.z + 10 + 24 * (i / 4), 0.5f);
     r.viewDepthField = view ? 1 : 0;
     r.updateUniforms();
+    for (int f = 0; f < walk; f++) {                          // main.cpp:58-66 with scripted input at a fixed 60 fps
+        r.draw();
+        r.keys[KEY_W] = true; r.keys[LMB] = true;             // walk forward while turning (mouse right of / below the centre)
+        r.mouseX = W / 2 + W / 20; r.mouseY = H / 2 + H / 60;
+        r.keys[SPACE] = f % 45 == 0;
+        if (f == walk / 2) r.keys[KEY_T] = true;              // drop a light half way
+        if (f == walk - 1) r.keys[RMB] = true;                // and dig on the last frame
+        r.movementUpdate(); r.doMouseLook(); r.doGravity();
+        if (r.keys[RMB]) { r.keys[RMB] = false; r.doDestroy(); }
+        r.updateUniforms();
+    }
+    if (walk) printf("walk %d: cam %a %a %a dir %a %a %a rot %a %a\n", walk, r.camPos.x, r.camPos.y, r.camPos.z, r.camDir.x, r.camDir.y, r.camDir.z,
+                     r.camRotation.x, r.camRotation.y);
     double ms_sum = 0;
     for (int f = 0; f < frames; f++) {                        // main.cpp:58-72 without the window
         r.draw();
@@ -47,7 +61,7 @@ int main(int argc, char** argv) {
         r.updateUniforms();
         ms_sum += r.stats().ms_total;
     }
-    if (destroy || frames > 1) r.draw();                      // show the state after the last update
+    if (destroy || walk || frames > 1) r.draw();                      // show the state after the last update
     const vxrt_stats s = r.stats();
     printf("init %.3f s; %d frame(s) %dx%d: %.3f ms/frame (device), last frame: %llu rays, %llu voxel fetches\n", init_s, frames, W, H,
            ms_sum / frames, (unsigned long long)(s.rays_primary + s.rays_global + s.rays_local), (unsigned long long)s.fetches);

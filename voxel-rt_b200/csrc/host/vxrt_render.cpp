@@ -141,6 +141,35 @@ void Render::setMouseLook(float rx, float ry) {
     camDir = vec3{rotateMatrix[8] + rotateMatrix[12], rotateMatrix[9] + rotateMatrix[13], rotateMatrix[10] + rotateMatrix[14]};   // * vec4(0,0,1,1)
 }
 
+// ---- gameplay: the Player of vxrt_controls.cpp works on this object's "globals" ----
+void Render::toPlayer() {
+    player_.cam_pos[0] = camPos.x; player_.cam_pos[1] = camPos.y; player_.cam_pos[2] = camPos.z;
+    player_.cam_dir[0] = camDir.x; player_.cam_dir[1] = camDir.y; player_.cam_dir[2] = camDir.z;
+    player_.cam_rotation[0] = camRotation.x; player_.cam_rotation[1] = camRotation.y;
+    memcpy(player_.rotate_matrix.m, rotateMatrix, sizeof rotateMatrix);
+    player_.view_depth_field = viewDepthField;
+    for (int k = 0; k < KEYS; k++) player_.keys[k] = keys[k];
+    player_.fps = fps; player_.mouse_x = mouseX; player_.mouse_y = mouseY; player_.screen_w = screenWidth; player_.screen_h = screenHeight;
+    player_.voxels = voxels.data(); player_.w = VOXELS_WIDTH; player_.h = VOXELS_HEIGHT; player_.d = VOXELS_DEPTH;
+}
+
+void Render::fromPlayer() {
+    camPos = vec3{player_.cam_pos[0], player_.cam_pos[1], player_.cam_pos[2]};
+    camDir = vec3{player_.cam_dir[0], player_.cam_dir[1], player_.cam_dir[2]};
+    camRotation = vec2{player_.cam_rotation[0], player_.cam_rotation[1]};
+    memcpy(rotateMatrix, player_.rotate_matrix.m, sizeof rotateMatrix);
+    viewDepthField = player_.view_depth_field;
+    for (int k = 0; k < KEYS; k++) keys[k] = player_.keys[k];
+    if (player_.light_requested) {                            // controls.cpp:46-49
+        player_.light_requested = false;
+        placeLocalLight(player_.light_pos[0], player_.light_pos[1], player_.light_pos[2], 0.5f);
+    }
+}
+
+void Render::movementUpdate() { toPlayer(); player_.movementUpdate(); fromPlayer(); }
+void Render::doGravity() { toPlayer(); player_.doGravity(); fromPlayer(); }
+void Render::doMouseLook() { toPlayer(); player_.doMouseLook(); fromPlayer(); }
+
 void Render::updateUniforms() {
     vxrt_frame f{};
     f.cam_pos[0] = camPos.x; f.cam_pos[1] = camPos.y; f.cam_pos[2] = camPos.z;

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../../include/vxrt.h"
+#include "vxrt_controls.hpp"
 
 namespace vxrt_host {
 
@@ -38,6 +39,8 @@ public:
     float lightRotation = -45.0f;                                      // main.cpp:36
     int viewDepthField = 0;
     float localLights[MAX_LOCAL_LIGHTS][4];
+    bool keys[KEYS] = {};                                              // main.cpp:15
+    int mouseX = 0, mouseY = 0;                                        // main.cpp:9-10
 
     Render() = default;
     ~Render();
@@ -61,6 +64,9 @@ public:
     // ---- what main.cpp / controls.cpp do around it ----
     void draw();                                             // glDrawArrays(GL_TRIANGLES,0,6) main.cpp:59
     void doDestroy();                                        // controls.cpp:100-110 body (the RMB branch)
+    void movementUpdate();                                   // controls.cpp:22-74   } host code on the grid mirror
+    void doGravity();                                        // controls.cpp:77-98   } (vxrt_controls.cpp), state
+    void doMouseLook();                                      // controls.cpp:112-144 } synced with the members above
     void setMouseLook(float rotX, float rotY);               // controls.cpp:137-142: rotateMatrix = rotY*rotX, camDir
     bool writePPM(const std::string& path);                  // headless "swap buffers"
     bool readPixels(std::vector<uint8_t>& rgba);             // bottom-up RGBA8
@@ -73,7 +79,10 @@ public:
 private:
     vxrt_ctx* ctx_ = nullptr;
     std::string err_;
+    Player player_;
     void check(int rc);
+    void toPlayer();
+    void fromPlayer();
 };
 
 }  // namespace vxrt_host
