@@ -239,6 +239,13 @@ int ref_host_player_get(float out24[24]) {
     memcpy(out24 + 8, glm::value_ptr(rotateMatrix), 64);
     return viewDepthField;
 }
+// n calls of the reference's lightUpdate() (render.cpp:388-402) from a given angle; out = lightRotation, lightPos[3]
+void ref_host_light_update(long long fps_, float rotation, int n, float out4[4]) {
+    fps = fps_;
+    lightRotation = rotation;
+    for (int i = 0; i < n; i++) lightUpdate();
+    out4[0] = lightRotation; out4[1] = lightPos.x; out4[2] = lightPos.y; out4[3] = lightPos.z;
+}
 void ref_host_init_lights(void) { initLocalLights(); }
 int ref_host_collided(const float cam[3]) { camPos = glm::vec3(cam[0], cam[1], cam[2]); return collided(); }
 

@@ -51,3 +51,8 @@ def run_case(player_reset, player_step, case, take_light=None):
             if l is not None:
                 lights.append(l.copy())
     return states, lights
+
+
+# lightUpdate (render.cpp:388-402): (fps, start angle in degrees, calls) -- covers day, the 8x night branch and the wrap
+SUN_CASES = [(60, -45.0, 1), (60, -45.0, 1000), (30, 179.9, 50), (144, 269.95, 400), (60, 359.99, 10), (75, 200.0, 2000), (240, 90.0, 5000)]
+LOOK_CASES = [(0.0, 0.0), (0.5, 0.6), (-1.57, 3.0), (1.2, -6.1), (0.001, 6.28), (-0.7, -2.4)]

@@ -1,7 +1,7 @@
 """Generates tests/golden/golden_controls.json from the REFERENCE's own controls.cpp (oracle/_ref/libref_host.so,
 built by `make -C oracle ref`): for every scripted input sequence of tests/controls_cases.py the FNV-1a-64 of all
 per-frame states (camPos, camDir, camRotation, rotateMatrix, viewDepthField as float32 bits), a few sampled states
-and the final local-light table.  Run in the build container (needs /root/reference):
+and the final local-light table; plus lightUpdate (sun) and doMouseLook matrix known answers.  Run in the build container (needs /root/reference):
 
     python tests/golden/make_golden_controls.py
 """
@@ -35,6 +35,8 @@ def main():
         samples = {str(i): [float(v).hex() for v in states[i]] for i in (0, len(states) // 3, 2 * len(states) // 3, len(states) - 1)}
         out[name] = dict(frames=len(states), fnv="%016x" % fnv(states), samples=samples,
                          lights=[[float(v).hex() for v in row] for row in rh.lights()])
+    out["_sun"] = [[float(v).hex() for v in rh.light_update(*c)] for c in cc.SUN_CASES]
+    out["_look"] = [[float(v).hex() for v in np.concatenate(rh.mouse_look(*c))] for c in cc.LOOK_CASES]
     with open(os.path.join(HERE, "golden_controls.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", len(out), "cases")

@@ -236,6 +236,11 @@ class RefHost:
     def collided(self, cam):
         return self.L.ref_host_collided((C.c_float * 3)(*cam))
 
+    def light_update(self, fps, rotation, n):
+        out = np.zeros(4, np.float32)
+        self.L.ref_host_light_update(C.c_longlong(fps), C.c_float(rotation), C.c_int(n), _ptr(out, C.c_float))
+        return out
+
 
 class HostLogic:
     """voxel-rt_b200/libvxrt_hostlogic.so: the product's host gameplay code (CPU only, no device calls)."""
@@ -265,6 +270,17 @@ class HostLogic:
 
     def collided(self, cam):
         return self.L.vxh_player_collided(self.p, (C.c_float * 3)(*cam))
+
+    def light_update(self, fps, rotation, n, start=(256.0, 1536.0, 256.0)):
+        out = np.zeros(4, np.float32)
+        self.L.vxh_light_update(C.c_longlong(fps), C.c_float(rotation), (C.c_float * 3)(*start), C.c_int(n), _ptr(out, C.c_float))
+        return out
+
+    def mouse_look(self, rx, ry):
+        rot = np.zeros(16, np.float32)
+        d = np.zeros(3, np.float32)
+        self.L.vxh_mouse_look_matrix(C.c_float(rx), C.c_float(ry), _ptr(rot, C.c_float), _ptr(d, C.c_float))
+        return rot, d
 
     def rotate(self, angle, axis):
         out = np.zeros(16, np.float32)

@@ -77,3 +77,15 @@ def test_headless_scripted_walk(vx, oracle, default_level, tmp_path):
     fr = ol.make_frame(st[0:3], rotate=st[8:24], aspect=np.float32(W) / np.float32(H), lights=lt, cam_rotation=(float(st[6]), float(st[7])))
     got = np.fromfile(raw, np.uint8).reshape(H, W, 4)
     assert np.array_equal(got, oracle.render(level, gc.DIMS, fr, W, H)["rgba8"])
+
+
+def test_headless_sun_moves_between_frames(vx, oracle, default_level, tmp_path):
+    """main.cpp:58-61: lightUpdate() after every draw; the frame after N updates uses the reference's sun position"""
+    W, H, N = 256, 144, 40
+    raw, _, _ = run_headless(vx, tmp_path, "--size", W, H, "--frames", N)
+    hl = ol.HostLogic(default_level, gc.DIMS)
+    sun = hl.light_update(60, -45.0, N)
+    hl.close()
+    fr = ol.make_frame(gc.CAM, light_pos=sun[1:4], aspect=np.float32(W) / np.float32(H))
+    got = np.fromfile(raw, np.uint8).reshape(H, W, 4)
+    assert np.array_equal(got, oracle.render(default_level, gc.DIMS, fr, W, H)["rgba8"])

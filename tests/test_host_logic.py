@@ -48,6 +48,18 @@ def golden_controls():
         return json.load(f)
 
 
+def _bits(vals):
+    return np.array([float.fromhex(v) for v in vals], np.float32).view(np.uint32)
+
+
+def test_sun_and_mouse_look_match_reference_golden(logic, golden_controls):
+    """lightUpdate (render.cpp:388-402) and doMouseLook's matrix (controls.cpp:137-142)"""
+    for c, want in zip(cc.SUN_CASES, golden_controls["_sun"]):
+        assert np.array_equal(logic.light_update(*c).view(np.uint32), _bits(want)), c
+    for c, want in zip(cc.LOOK_CASES, golden_controls["_look"]):
+        assert np.array_equal(np.concatenate(logic.mouse_look(*c)).view(np.uint32), _bits(want)), c
+
+
 @pytest.mark.parametrize("name", sorted(cc.cases()))
 def test_trajectory_matches_reference_golden(logic, golden_controls, name):
     case = cc.cases()[name]
@@ -133,5 +145,9 @@ def test_rotate_and_collided_match_reference_live(logic):
             assert np.array_equal(mine.rotate(rx, (1, 0, 0)), rot)      # rotY(0) * rotX = rotX exactly
             cam = (rng.uniform(1, 510), rng.uniform(11, 94), rng.uniform(1, 510))
             assert mine.collided(cam) == rh.collided(cam)
+            a, b = rh.mouse_look(rx, ry), mine.mouse_look(rx, ry)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+            sun = (int(rng.integers(20, 240)), float(rng.uniform(-45, 361)), int(rng.integers(1, 300)))
+            assert np.array_equal(rh.light_update(*sun).view(np.uint32), mine.light_update(*sun).view(np.uint32)), sun
     finally:
         mine.close()

@@ -64,6 +64,28 @@ void vec4_mul_mat4(const float v[4], const Mat4& m, float out[4]) {
         out[c] = ((m.m[4 * c] * v[0] + m.m[4 * c + 1] * v[1]) + m.m[4 * c + 2] * v[2]) + m.m[4 * c + 3] * v[3];
 }
 
+void light_update(long long fps, float& light_rotation, const float start[3], float light_pos[3]) {   // render.cpp:388-402
+    float increment = 0.3f / fps;
+    if (light_rotation >= 360.0f) light_rotation = 0.0f;
+    else if (light_rotation >= 180.0f && light_rotation < 270.0f) increment *= 8.0f;
+    light_rotation += increment;
+    const Mat4 rot = mat4_rotate(mat4_identity(), light_rotation * 0.01745329251994329576923690768489f, 0, 0, 1);
+    const float v[4] = {start[0], start[1], start[2], 1.0f};
+    float o[4];
+    mat4_mul_vec4(rot, v, o);
+    light_pos[0] = o[0]; light_pos[1] = o[1]; light_pos[2] = o[2];
+}
+
+void mouse_look_matrix(float rx, float ry, Mat4& rotate, float cam_dir[3]) {     // controls.cpp:137-142
+    const Mat4 rotX = mat4_rotate(mat4_identity(), rx, 1, 0, 0);
+    const Mat4 rotY = mat4_rotate(mat4_identity(), ry, 0, 1, 0);
+    rotate = mat4_mul(rotY, rotX);
+    const float f[4] = {0, 0, 1, 1};
+    float o[4];
+    mat4_mul_vec4(rotate, f, o);
+    cam_dir[0] = o[0]; cam_dir[1] = o[1]; cam_dir[2] = o[2];
+}
+
 int Player::voxel_at(int x, int y, int z) const {
     if (x >= 0 && y >= 0 && z >= 0 && x < w && y < h && z < d) return voxels[x + w * y + w * h * z];
     return 0;                           // getVoxelIndex() == -1: the reference reads voxels[-1], zero in its build => solid
@@ -135,13 +157,7 @@ void Player::doMouseLook() {                                // controls.cpp:112-
         if (cam_rotation[0] >= 2 * PI) cam_rotation[0] = 0.0f; else if (cam_rotation[0] <= -2 * PI) cam_rotation[0] = 0.0f;
         if (cam_rotation[1] >= 2 * PI) cam_rotation[1] = 0.0f; else if (cam_rotation[1] <= -2 * PI) cam_rotation[1] = 0.0f;
         cam_rotation[0] = std::fmin(PI / 2.0f, std::fmax(-PI / 2.0f, cam_rotation[0]));
-        const Mat4 rotX = mat4_rotate(mat4_identity(), cam_rotation[0], 1, 0, 0);
-        const Mat4 rotY = mat4_rotate(mat4_identity(), cam_rotation[1], 0, 1, 0);
-        rotate_matrix = mat4_mul(rotY, rotX);
-        const float f[4] = {0, 0, 1, 1};
-        float o[4];
-        mat4_mul_vec4(rotate_matrix, f, o);
-        cam_dir[0] = o[0]; cam_dir[1] = o[1]; cam_dir[2] = o[2];
+        mouse_look_matrix(cam_rotation[0], cam_rotation[1], rotate_matrix, cam_dir);
     }
 }
 
@@ -178,5 +194,16 @@ int vxh_player_take_light(Player* p, float out3[3]) {
     return 1;
 }
 int vxh_player_collided(Player* p, const float cam[3]) { for (int k = 0; k < 3; k++) p->cam_pos[k] = cam[k]; return p->collided(); }
+// n calls of lightUpdate from the given angle; out = lightRotation, lightPos[3]
+void vxh_light_update(long long fps, float rotation, const float start[3], int n, float out4[4]) {
+    float pos[3] = {start[0], start[1], start[2]};
+    for (int i = 0; i < n; i++) light_update(fps, rotation, start, pos);
+    out4[0] = rotation; out4[1] = pos[0]; out4[2] = pos[1]; out4[3] = pos[2];
+}
+void vxh_mouse_look_matrix(float rx, float ry, float rot16[16], float dir3[3]) {
+    Mat4 m;
+    mouse_look_matrix(rx, ry, m, dir3);
+    for (int k = 0; k < 16; k++) rot16[k] = m.m[k];
+}
 void vxh_mat4_rotate(float angle, float ax, float ay, float az, float out16[16]) { Mat4 r = mat4_rotate(mat4_identity(), angle, ax, ay, az); for (int k = 0; k < 16; k++) out16[k] = r.m[k]; }
 }

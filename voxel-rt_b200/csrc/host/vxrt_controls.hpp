@@ -20,6 +20,12 @@ Mat4 mat4_mul(const Mat4& a, const Mat4& b);                                  //
 void mat4_mul_vec4(const Mat4& m, const float v[4], float out[4]);            // operator*(mat4, vec4)
 void vec4_mul_mat4(const float v[4], const Mat4& m, float out[4]);            // operator*(vec4, mat4)
 
+// lightUpdate(), render.cpp:388-402: advances the sun angle (degrees; night runs 8x faster, wraps at 360) and
+// rotates the start position about +z
+void light_update(long long fps, float& light_rotation, const float start_light_pos[3], float light_pos[3]);
+// doMouseLook's matrix for given angles (controls.cpp:137-142): rotate = rotY * rotX, dir = rotate * (0,0,1,1)
+void mouse_look_matrix(float rot_x, float rot_y, Mat4& rotate, float cam_dir[3]);
+
 struct Player {
     // state the reference keeps in globals (main.cpp:20-37, controls.cpp:8)
     float cam_pos[3] = {195, 55, 155};

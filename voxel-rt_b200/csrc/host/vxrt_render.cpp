@@ -107,38 +107,20 @@ void Render::placeLocalLight(float x, float y, float z, float diffuse) {
         }
 }
 
-// glm::rotate(mat4(1), angle, axis) for the unit axes (glm/ext/matrix_transform.inl:18-47), column-major
-static void rotation(float angle, int axis, float m[16]) {
-    const float c = std::cos(angle), s = std::sin(angle);
-    for (int i = 0; i < 16; i++) m[i] = (i % 5 == 0) ? 1.0f : 0.0f;
-    const int a = (axis + 1) % 3, b = (axis + 2) % 3;
-    m[4 * a + a] = c; m[4 * a + b] = s; m[4 * b + a] = -s; m[4 * b + b] = c;
+void Render::lightUpdate() {                                  // render.cpp:388-402 (vxrt_controls.cpp: light_update)
+    const float start[3] = {startLightPos.x, startLightPos.y, startLightPos.z};
+    float pos[3];
+    light_update(fps, lightRotation, start, pos);
+    lightPos = vec3{pos[0], pos[1], pos[2]};
 }
 
-void Render::lightUpdate() {
-    float increment = 0.3f / fps;                            // render.cpp:389
-    if (lightRotation >= 360.0f) lightRotation = 0.0f;
-    else if (lightRotation >= 180.0f && lightRotation < 270.0f) increment *= 8.0f;
-    lightRotation += increment;
-    float rot[16];
-    rotation(lightRotation * 0.01745329251994329576923690768489f, 2, rot);      // glm::radians
-    const float v[4] = {startLightPos.x, startLightPos.y, startLightPos.z, 1.0f};
-    float o[3];
-    for (int r = 0; r < 3; r++) o[r] = (rot[r] * v[0] + rot[4 + r] * v[1]) + (rot[8 + r] * v[2] + rot[12 + r] * v[3]);
-    lightPos = vec3{o[0], o[1], o[2]};
-}
-
-void Render::setMouseLook(float rx, float ry) {
+void Render::setMouseLook(float rx, float ry) {               // controls.cpp:137-142
     camRotation = vec2{rx, ry};
-    float X[16], Y[16];
-    rotation(rx, 0, X); rotation(ry, 1, Y);
-    for (int c = 0; c < 4; c++)                               // rotateMatrix = rotY * rotX
-        for (int r = 0; r < 4; r++) {
-            float acc = 0.0f;
-            for (int k = 0; k < 4; k++) acc += Y[4 * k + r] * X[4 * c + k];
-            rotateMatrix[4 * c + r] = acc;
-        }
-    camDir = vec3{rotateMatrix[8] + rotateMatrix[12], rotateMatrix[9] + rotateMatrix[13], rotateMatrix[10] + rotateMatrix[14]};   // * vec4(0,0,1,1)
+    Mat4 m;
+    float dir[3];
+    mouse_look_matrix(rx, ry, m, dir);
+    memcpy(rotateMatrix, m.m, sizeof rotateMatrix);
+    camDir = vec3{dir[0], dir[1], dir[2]};
 }
 
 // ---- gameplay: the Player of vxrt_controls.cpp works on this object's "globals" ----
