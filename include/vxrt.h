@@ -102,6 +102,14 @@ int vxrt_download_grid(vxrt_ctx* ctx, int32_t* out, size_t count);
 /* copy the device box [lo,hi) (clamped to the grid) into the caller's FULL-GRID array (host mirror sync after
    a device-side edit; the reference's CPU collision code reads voxels[], controls.cpp:10-19) */
 int vxrt_download_box(vxrt_ctx* ctx, const int32_t lo[3], const int32_t hi[3], int32_t* host_voxels);
+/* Grid files (the reference has no on-disk format, its level exists only as level.cpp's generator):
+   a 64-byte little-endian header -- "VXRTGRD1", uint32 w, h, d, flags(0), uint64 count, uint64 FNV-1a-64 of the
+   payload, 24 reserved zero bytes -- followed by count int32 voxels in the reference's order (x + w*y + w*h*z).
+   save streams the device grid to the file; load checks extents against the context and the fingerprint against the
+   payload (VXRT_ERR_IO on a short / corrupt file, after which the context has no grid) and leaves the grid on the
+   device as vxrt_upload_grid would.  voxel-rt_b200/gridfile.py reads and writes the same format on the host. */
+int vxrt_save_grid(vxrt_ctx* ctx, const char* path);
+int vxrt_load_grid(vxrt_ctx* ctx, const char* path);
 
 /* placeVoxel render.cpp:256-262 / destroyVoxel render.cpp:265-271 applied to the device grid */
 int vxrt_place_voxel(vxrt_ctx* ctx, int x, int y, int z, int32_t voxel);

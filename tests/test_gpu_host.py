@@ -89,3 +89,18 @@ def test_headless_sun_moves_between_frames(vx, oracle, default_level, tmp_path):
     fr = ol.make_frame(gc.CAM, light_pos=sun[1:4], aspect=np.float32(W) / np.float32(H))
     got = np.fromfile(raw, np.uint8).reshape(H, W, 4)
     assert np.array_equal(got, oracle.render(default_level, gc.DIMS, fr, W, H)["rgba8"])
+
+
+def test_headless_saves_the_edited_level(vx, oracle, default_level, tmp_path):
+    """--destroy then --save: the file holds the reference default level after the reference's right-click edit; a second
+    run that --loads it renders the same frame"""
+    W, H = 160, 90
+    path = os.path.join(str(tmp_path), "edited.vxg")
+    raw, _, _ = run_headless(vx, tmp_path, "--size", W, H, "--destroy", "--save", path)
+    first = np.fromfile(raw, np.uint8).copy()
+    level = default_level.copy()
+    oracle.do_destroy(level, gc.DIMS, gc.CAM, (0.0, -1.0, 0.0))
+    got, dims = vx.gridfile.read_grid(path)
+    assert dims == gc.DIMS and np.array_equal(got, level)
+    raw, _, _ = run_headless(vx, tmp_path, "--size", W, H, "--load", path)
+    assert np.array_equal(np.fromfile(raw, np.uint8), first)

@@ -517,6 +517,67 @@ def test_peer_memory_frame_target_protocol_on_one_gpu(vx, oracle, default_level)
             r.close()
 
 
+# ---- grid files ------------------------------------------------------------------------------------
+def test_grid_file_round_trip_through_the_device(vx, oracle, default_level, tmp_path):
+    """vxrt_save_grid / vxrt_load_grid against the host-side reader / writer of the same format (gridfile.py)"""
+    W, H = 192, 108
+    p1, p2 = str(tmp_path / "dev.vxg"), str(tmp_path / "host.vxg")
+    fr = ol.make_frame(gc.CAM, aspect=np.float32(W) / np.float32(H), lights=gc.lights_4x4(gc.CAM))
+    with vx.Renderer(grid=gc.DIMS, width=W, height=H) as r:
+        r.initVoxels(); r.buildDepthField()                 # device-generated level
+        r.removeSphere((195, 40, 165), 7)
+        r.saveGrid(p1)
+        edited = r.downloadGrid()
+    hd = vx.gridfile.read_header(p1)
+    assert hd["dims"] == gc.DIMS and hd["fnv"] == oracle.fnv(edited)
+    got, _ = vx.gridfile.read_grid(p1)
+    assert np.array_equal(got, edited)
+    want_level = default_level.copy()
+    oracle.remove_sphere(want_level, gc.DIMS, 195, 40, 165, 7)
+    assert np.array_equal(got, want_level)
+    vx.gridfile.write_grid(p2, default_level, gc.DIMS)     # host-written file -> device
+    with vx.Renderer(grid=gc.DIMS, width=W, height=H) as r:
+        r.loadGrid(p2)
+        assert np.array_equal(r.downloadGrid(), default_level)
+        r.updateUniforms(fr); r.draw()
+        assert np.array_equal(r.readPixels(), oracle.render(default_level, gc.DIMS, fr, W, H)["rgba8"])
+        r.loadGrid(p1)                                       # and the device-written one (culling summary must follow)
+        r.draw()
+        assert np.array_equal(r.readPixels(), oracle.render(want_level, gc.DIMS, fr, W, H)["rgba8"])
+
+
+def test_grid_file_errors(vx, tmp_path):
+    rng = np.random.default_rng(4)
+    dims = (16, 8, 12)
+    v = rng.integers(-1, 100, size=16 * 8 * 12, dtype=np.int32)
+    good = str(tmp_path / "good.vxg")
+    vx.gridfile.write_grid(good, v, dims)
+    raw = bytearray(open(good, "rb").read())
+    with vx.Renderer(grid=dims, width=32, height=8) as r:
+        with pytest.raises(vx.VxrtError, match="before any grid upload"):
+            r.saveGrid(str(tmp_path / "none.vxg"))
+        with pytest.raises(vx.VxrtError, match="cannot open"):
+            r.loadGrid(str(tmp_path / "missing.vxg"))
+        r.loadGrid(good)
+        assert np.array_equal(r.downloadGrid(), v)
+        flipped = bytearray(raw); flipped[64 + 5] ^= 1
+        open(str(tmp_path / "flip.vxg"), "wb").write(bytes(flipped))
+        with pytest.raises(vx.VxrtError, match="fingerprint"):
+            r.loadGrid(str(tmp_path / "flip.vxg"))
+        with pytest.raises(vx.VxrtError, match="before any grid upload"):      # a failed load leaves no grid in use
+            r.draw()
+        open(str(tmp_path / "short.vxg"), "wb").write(bytes(raw[:-4]))
+        with pytest.raises(vx.VxrtError, match="shorter"):
+            r.loadGrid(str(tmp_path / "short.vxg"))
+        open(str(tmp_path / "magic.vxg"), "wb").write(b"NOTAGRID" + bytes(raw[8:]))
+        with pytest.raises(vx.VxrtError, match="VXRTGRD1"):
+            r.loadGrid(str(tmp_path / "magic.vxg"))
+        r.loadGrid(good); r.draw()
+    with vx.Renderer(grid=(16, 8, 13), width=32, height=8) as r:
+        with pytest.raises(vx.VxrtError, match="extents"):
+            r.loadGrid(good)
+
+
 # ---- API state / error behaviour -----------------------------------------------------------------
 def test_errors_are_loud(vx):
     with vx.Renderer(grid=(16, 16, 16), width=32, height=8) as r:

@@ -2,7 +2,7 @@
 hand-written CUDA behind a C ABI (include/vxrt.h), plus the host-side mirror of src/render.hpp."""
 from .api import (Renderer, Frame, Config, Stats, VxrtError, make_frame, load_library,
                   MAX_LOCAL_LIGHTS, TILE_W, TILE_H)
-from . import scenes, tiles
+from . import scenes, tiles, gridfile
 
 __all__ = ["Renderer", "Frame", "Config", "Stats", "VxrtError", "make_frame", "load_library",
            "MAX_LOCAL_LIGHTS", "TILE_W", "TILE_H", "scenes", "tiles"]

@@ -58,6 +58,8 @@ _SIGNATURES = {
     "vxrt_update_partial": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.POINTER(C.c_int32)]),
     "vxrt_download_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "vxrt_download_box": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]),
+    "vxrt_save_grid": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "vxrt_load_grid": (C.c_int, [C.c_void_p, C.c_char_p]),
     "vxrt_place_voxel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int32]),
     "vxrt_destroy_voxel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "vxrt_edit_remove_sphere": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -262,6 +264,13 @@ class Renderer:
         l = (C.c_int32 * 3)(*[int(v) for v in lo])
         h = (C.c_int32 * 3)(*[int(v) for v in hi])
         self._check(self.lib.vxrt_download_box(self._h, l, h, _vp(host_voxels)))
+
+    def saveGrid(self, path):
+        """device grid -> VXRTGRD1 file (gridfile.py reads it on the host)"""
+        self._check(self.lib.vxrt_save_grid(self._h, os.fsencode(path)))
+
+    def loadGrid(self, path):
+        self._check(self.lib.vxrt_load_grid(self._h, os.fsencode(path)))
 
     def updateUniforms(self, frame):
         self._check(self.lib.vxrt_set_frame(self._h, C.byref(frame)))

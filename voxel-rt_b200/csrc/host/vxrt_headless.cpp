@@ -1,7 +1,7 @@
 // vxrt_headless.cpp -- the reference's game loop (src/main.cpp:47-75) run headless on the B200 path: no window,
 // frames go to PPM files / a raw RGBA8 dump instead of glfwSwapBuffers.  Used by tests/test_gpu_host.py.
 //
-//   vxrt_headless [--size W H] [--frames N] [--lights] [--pitched] [--view] [--destroy] [--walk N] [--ppm out.ppm] [--raw out.rgba]
+//   vxrt_headless [--size W H] [--frames N] [--lights] [--pitched] [--view] [--destroy] [--walk N] [--load in.vxg] [--save out.vxg] [--ppm out.ppm] [--raw out.rgba]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -15,7 +15,7 @@ using namespace vxrt_host;
 int main(int argc, char** argv) {
     int W = 1280, H = 720, frames = 1, walk = 0;
     bool lights = false, pitched = false, view = false, destroy = false;
-    std::string ppm, raw;
+    std::string ppm, raw, load, save;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         if (a == "--size" && i + 2 < argc) { W = atoi(argv[++i]); H = atoi(argv[++i]); }
@@ -25,6 +25,8 @@ int main(int argc, char** argv) {
         else if (a == "--view") view = true;
         else if (a == "--destroy") destroy = true;
         else if (a == "--walk" && i + 1 < argc) walk = atoi(argv[++i]);
+        else if (a == "--load" && i + 1 < argc) load = argv[++i];
+        else if (a == "--save" && i + 1 < argc) save = argv[++i];
         else if (a == "--ppm" && i + 1 < argc) ppm = argv[++i];
         else if (a == "--raw" && i + 1 < argc) raw = argv[++i];
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
@@ -34,6 +36,7 @@ int main(int argc, char** argv) {
     const auto t0 = std::chrono::steady_clock::now();
     r.initRender();                                           // main.cpp:55
     const double init_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!load.empty() && !r.loadGrid(load)) { fprintf(stderr, "%s\n", r.lastError().c_str()); return 1; }
     if (pitched) { r.camPos = vec3{195, 60, 155}; r.setMouseLook(0.5f, 0.6f); }
     if (lights)
         for (int i = 0; i < 16; i++)                          // T key, controls.cpp:46-49, on the 4x4 pattern of SURVEY.md 8d
@@ -65,6 +68,7 @@ int main(int argc, char** argv) {
     const vxrt_stats s = r.stats();
     printf("init %.3f s; %d frame(s) %dx%d: %.3f ms/frame (device), last frame: %llu rays, %llu voxel fetches\n", init_s, frames, W, H,
            ms_sum / frames, (unsigned long long)(s.rays_primary + s.rays_global + s.rays_local), (unsigned long long)s.fetches);
+    if (!save.empty() && !r.saveGrid(save)) { fprintf(stderr, "%s\n", r.lastError().c_str()); return 1; }
     if (!ppm.empty() && !r.writePPM(ppm)) return 1;
     if (!raw.empty()) {
         std::vector<uint8_t> px;

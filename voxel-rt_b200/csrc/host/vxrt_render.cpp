@@ -172,6 +172,19 @@ void Render::reshape(int width, int height) {
 
 void Render::draw() { check(vxrt_render(ctx_)); }
 
+bool Render::saveGrid(const std::string& path) {
+    const int rc = vxrt_save_grid(ctx_, path.c_str());
+    if (rc != VXRT_OK) err_ = vxrt_last_error();
+    return rc == VXRT_OK;
+}
+
+bool Render::loadGrid(const std::string& path) {
+    int rc = vxrt_load_grid(ctx_, path.c_str());
+    if (rc == VXRT_OK) rc = vxrt_download_grid(ctx_, voxels.data(), voxels.size());    // keep the collision mirror coherent
+    if (rc != VXRT_OK) err_ = vxrt_last_error();
+    return rc == VXRT_OK;
+}
+
 bool Render::writePPM(const std::string& path) { const int rc = vxrt_write_ppm(ctx_, path.c_str()); check(rc); return rc == 0; }
 
 bool Render::readPixels(std::vector<uint8_t>& rgba) {

@@ -68,6 +68,8 @@ public:
     void doGravity();                                        // controls.cpp:77-98   } (vxrt_controls.cpp), state
     void doMouseLook();                                      // controls.cpp:112-144 } synced with the members above
     void setMouseLook(float rotX, float rotY);               // controls.cpp:137-142: rotateMatrix = rotY*rotX, camDir
+    bool saveGrid(const std::string& path);                  // device grid -> VXRTGRD1 file (include/vxrt.h)
+    bool loadGrid(const std::string& path);                  // file -> device grid + host mirror
     bool writePPM(const std::string& path);                  // headless "swap buffers"
     bool readPixels(std::vector<uint8_t>& rgba);             // bottom-up RGBA8
     vxrt_stats stats();

@@ -401,6 +401,86 @@ extern "C" int vxrt_download_grid(vxrt_ctx* c, int32_t* out, size_t count) {
     return VXRT_OK;
 }
 
+// ---- grid files -------------------------------------------------------------------------------
+struct GridFileHeader {                 // 64 bytes, little-endian (include/vxrt.h)
+    char magic[8];
+    uint32_t w, h, d, flags;
+    uint64_t count, fnv;
+    uint8_t reserved[24];
+};
+static_assert(sizeof(GridFileHeader) == 64, "grid file header is 64 bytes");
+static const size_t GRID_FILE_CHUNK = (size_t)8 << 20;      // voxels per staged copy (32 MiB)
+
+static uint64_t fnv1a64_update(uint64_t h, const void* data, size_t nbytes) {
+    const uint8_t* p = (const uint8_t*)data;
+    for (size_t i = 0; i < nbytes; i++) { h ^= p[i]; h *= 0x100000001b3ull; }
+    return h;
+}
+
+extern "C" int vxrt_save_grid(vxrt_ctx* c, const char* path) {
+    CHECK_CTX(c);
+    if (!path) return fail(VXRT_ERR_INVALID, "save_grid: null path");
+    if (!c->grid_loaded) return fail(VXRT_ERR_STATE, "save_grid before any grid upload");
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return fail(VXRT_ERR_IO, std::string("save_grid: cannot open ") + path);
+    GridFileHeader hd;
+    memset(&hd, 0, sizeof hd);
+    memcpy(hd.magic, "VXRTGRD1", 8);
+    hd.w = (uint32_t)c->cfg.grid_w; hd.h = (uint32_t)c->cfg.grid_h; hd.d = (uint32_t)c->cfg.grid_d;
+    hd.count = c->nvox;
+    int32_t* stage = nullptr;
+    const size_t chunk = std::min(GRID_FILE_CHUNK, (size_t)c->nvox);
+    if (cudaMallocHost(&stage, chunk * 4) != cudaSuccess) { fclose(fp); cudaGetLastError(); return fail(VXRT_ERR_CUDA, "save_grid: pinned staging allocation failed"); }
+    bool ok = fwrite(&hd, sizeof hd, 1, fp) == 1;
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (size_t first = 0; ok && first < c->nvox; first += chunk) {
+        const size_t n = std::min(chunk, (size_t)c->nvox - first);
+        if (cudaMemcpyAsync(stage, c->d_vox + first, n * 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaFreeHost(stage); fclose(fp); return fail(VXRT_ERR_CUDA, "save_grid: device read failed"); }
+        h = fnv1a64_update(h, stage, n * 4);
+        ok = fwrite(stage, 4, n, fp) == n;
+    }
+    cudaFreeHost(stage);
+    hd.fnv = h;
+    ok = ok && fseek(fp, 0, SEEK_SET) == 0 && fwrite(&hd, sizeof hd, 1, fp) == 1;
+    ok = (fclose(fp) == 0) && ok;
+    if (!ok) return fail(VXRT_ERR_IO, std::string("save_grid: write failed on ") + path);
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_load_grid(vxrt_ctx* c, const char* path) {
+    CHECK_CTX(c);
+    if (!path) return fail(VXRT_ERR_INVALID, "load_grid: null path");
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(VXRT_ERR_IO, std::string("load_grid: cannot open ") + path);
+    GridFileHeader hd;
+    if (fread(&hd, sizeof hd, 1, fp) != 1 || memcmp(hd.magic, "VXRTGRD1", 8) != 0) { fclose(fp); return fail(VXRT_ERR_IO, "load_grid: not a VXRTGRD1 file"); }
+    if (hd.w != (uint32_t)c->cfg.grid_w || hd.h != (uint32_t)c->cfg.grid_h || hd.d != (uint32_t)c->cfg.grid_d || hd.count != (uint64_t)c->nvox) {
+        fclose(fp);
+        return fail(VXRT_ERR_INVALID, "load_grid: the file's extents differ from the context's grid");
+    }
+    int32_t* stage = nullptr;
+    const size_t chunk = std::min(GRID_FILE_CHUNK, (size_t)c->nvox);
+    if (cudaMallocHost(&stage, chunk * 4) != cudaSuccess) { fclose(fp); cudaGetLastError(); return fail(VXRT_ERR_CUDA, "load_grid: pinned staging allocation failed"); }
+    c->grid_loaded = false;                                  // a failed load leaves no half-written grid in use
+    uint64_t h = 0xcbf29ce484222325ull;
+    bool ok = true;
+    for (size_t first = 0; ok && first < c->nvox; first += chunk) {
+        const size_t n = std::min(chunk, (size_t)c->nvox - first);
+        ok = fread(stage, 4, n, fp) == n;
+        if (!ok) break;
+        h = fnv1a64_update(h, stage, n * 4);
+        if (cudaMemcpyAsync(c->d_vox + first, stage, n * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaFreeHost(stage); fclose(fp); return fail(VXRT_ERR_CUDA, "load_grid: device write failed"); }
+    }
+    cudaFreeHost(stage);
+    fclose(fp);
+    if (!ok) return fail(VXRT_ERR_IO, "load_grid: file shorter than its header says");
+    if (h != hd.fnv) return fail(VXRT_ERR_IO, "load_grid: payload fingerprint does not match the header");
+    c->grid_loaded = true;
+    return update_yrange(c, 0, c->nvox, true);
+}
+
 extern "C" int vxrt_download_box(vxrt_ctx* c, const int32_t lo[3], const int32_t hi[3], int32_t* host_voxels) {
     CHECK_CTX(c);
     if (!lo || !hi || !host_voxels) return fail(VXRT_ERR_INVALID, "download_box: null argument");
