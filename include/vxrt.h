@@ -84,7 +84,8 @@ int vxrt_device_available(void);
    any other host pointer works too, through an internal staging buffer */
 void* vxrt_host_alloc(size_t nbytes);
 void vxrt_host_free(void* p);
-/* FNV-1a-64 of a host buffer (grid fingerprints) */
+/* FNV-1a-64 of a host buffer as SURVEY.md 8c fingerprints grids (prime 1099511628211, offset basis
+   1469598103934665603) */
 uint64_t vxrt_fnv1a64(const void* data, size_t nbytes);
 
 /* ---- grid ------------------------------------------------------------------------------------- */
@@ -103,7 +104,7 @@ int vxrt_download_grid(vxrt_ctx* ctx, int32_t* out, size_t count);
    a device-side edit; the reference's CPU collision code reads voxels[], controls.cpp:10-19) */
 int vxrt_download_box(vxrt_ctx* ctx, const int32_t lo[3], const int32_t hi[3], int32_t* host_voxels);
 /* Grid files (the reference has no on-disk format, its level exists only as level.cpp's generator):
-   a 64-byte little-endian header -- "VXRTGRD1", uint32 w, h, d, flags(0), uint64 count, uint64 FNV-1a-64 of the
+   a 64-byte little-endian header -- "VXRTGRD1", uint32 w, h, d, flags(0), uint64 count, uint64 vxrt_fnv1a64 of the
    payload, 24 reserved zero bytes -- followed by count int32 voxels in the reference's order (x + w*y + w*h*z).
    save streams the device grid to the file; load checks extents against the context and the fingerprint against the
    payload (VXRT_ERR_IO on a short / corrupt file, after which the context has no grid) and leaves the grid on the

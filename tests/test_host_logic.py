@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def fnv(a):
-    h = 0xcbf29ce484222325
+    h = 1469598103934665603        # the survey's basis, as everywhere in this repo
     for b in np.ascontiguousarray(a).view(np.uint8).tobytes():
         h = ((h ^ b) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
     return h

@@ -254,12 +254,15 @@ extern "C" void* vxrt_host_alloc(size_t nbytes) {
 }
 extern "C" void vxrt_host_free(void* p) { if (p) cudaFreeHost(p); }
 
-extern "C" uint64_t vxrt_fnv1a64(const void* data, size_t nbytes) {
+// FNV-1a-64 as SURVEY.md 8c fingerprints grids: prime 1099511628211, offset basis 1469598103934665603 (the survey's
+// basis, one digit short of the textbook 14695981039346656037 -- kept, since every recorded fingerprint uses it)
+static const uint64_t FNV_BASIS = 1469598103934665603ull;
+static uint64_t fnv1a64_update(uint64_t h, const void* data, size_t nbytes) {
     const uint8_t* p = (const uint8_t*)data;
-    uint64_t h = 1469598103934665603ull;
     for (size_t i = 0; i < nbytes; i++) { h ^= p[i]; h *= 1099511628211ull; }
     return h;
 }
+extern "C" uint64_t vxrt_fnv1a64(const void* data, size_t nbytes) { return fnv1a64_update(FNV_BASIS, data, nbytes); }
 
 extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     if (!cfg || !out) return fail(VXRT_ERR_INVALID, "null argument");
@@ -317,6 +320,7 @@ extern "C" void vxrt_destroy(vxrt_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);     // before the buffers it copies from go away
     free_frame_buffers(c);
     if (c->p2p_base) { if (c->p2p_owner) cudaFree(c->p2p_base); else if (!c->p2p_attached) cudaIpcCloseMemHandle(c->p2p_base); }
     cudaFree(c->d_p2p_err);
@@ -328,7 +332,7 @@ extern "C" void vxrt_destroy(vxrt_ctx* c) {
     for (auto& e : c->ev_band) if (e) cudaEventDestroy(e);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     for (auto& e : c->ev_slot) if (e) cudaEventDestroy(e);
-    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -411,12 +415,6 @@ struct GridFileHeader {                 // 64 bytes, little-endian (include/vxrt
 static_assert(sizeof(GridFileHeader) == 64, "grid file header is 64 bytes");
 static const size_t GRID_FILE_CHUNK = (size_t)8 << 20;      // voxels per staged copy (32 MiB)
 
-static uint64_t fnv1a64_update(uint64_t h, const void* data, size_t nbytes) {
-    const uint8_t* p = (const uint8_t*)data;
-    for (size_t i = 0; i < nbytes; i++) { h ^= p[i]; h *= 0x100000001b3ull; }
-    return h;
-}
-
 extern "C" int vxrt_save_grid(vxrt_ctx* c, const char* path) {
     CHECK_CTX(c);
     if (!path) return fail(VXRT_ERR_INVALID, "save_grid: null path");
@@ -432,7 +430,7 @@ extern "C" int vxrt_save_grid(vxrt_ctx* c, const char* path) {
     const size_t chunk = std::min(GRID_FILE_CHUNK, (size_t)c->nvox);
     if (cudaMallocHost(&stage, chunk * 4) != cudaSuccess) { fclose(fp); cudaGetLastError(); return fail(VXRT_ERR_CUDA, "save_grid: pinned staging allocation failed"); }
     bool ok = fwrite(&hd, sizeof hd, 1, fp) == 1;
-    uint64_t h = 0xcbf29ce484222325ull;
+    uint64_t h = FNV_BASIS;
     for (size_t first = 0; ok && first < c->nvox; first += chunk) {
         const size_t n = std::min(chunk, (size_t)c->nvox - first);
         if (cudaMemcpyAsync(stage, c->d_vox + first, n * 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
@@ -463,7 +461,7 @@ extern "C" int vxrt_load_grid(vxrt_ctx* c, const char* path) {
     const size_t chunk = std::min(GRID_FILE_CHUNK, (size_t)c->nvox);
     if (cudaMallocHost(&stage, chunk * 4) != cudaSuccess) { fclose(fp); cudaGetLastError(); return fail(VXRT_ERR_CUDA, "load_grid: pinned staging allocation failed"); }
     c->grid_loaded = false;                                  // a failed load leaves no half-written grid in use
-    uint64_t h = 0xcbf29ce484222325ull;
+    uint64_t h = FNV_BASIS;
     bool ok = true;
     for (size_t first = 0; ok && first < c->nvox; first += chunk) {
         const size_t n = std::min(chunk, (size_t)c->nvox - first);
@@ -632,6 +630,7 @@ extern "C" int vxrt_resize(vxrt_ctx* c, int width, int height) {                
     if (width <= 0 || height <= 0) return fail(VXRT_ERR_INVALID, "resize: extents must be positive");
     if (c->p2p) return fail(VXRT_ERR_STATE, "resize: not available once a peer-memory target is set");
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));      // queued read-backs still read the buffers freed below
     c->cfg.width = width; c->cfg.height = height;
     c->frame.aspect = (float)width / height;
     return alloc_frame_buffers(c);
