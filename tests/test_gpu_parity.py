@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import golden_cases as gc
+import oracle_lib as ol
 
 pytestmark = pytest.mark.gpu
 
@@ -539,7 +540,7 @@ def test_grid_file_round_trip_through_the_device(vx, oracle, default_level, tmp_
     with vx.Renderer(grid=gc.DIMS, width=W, height=H) as r:
         r.loadGrid(p2)
         assert np.array_equal(r.downloadGrid(), default_level)
-        r.updateUniforms(fr); r.draw()
+        r.updateUniforms(to_vx_frame(vx, fr)); r.draw()
         assert np.array_equal(r.readPixels(), oracle.render(default_level, gc.DIMS, fr, W, H)["rgba8"])
         r.loadGrid(p1)                                       # and the device-written one (culling summary must follow)
         r.draw()

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __rest
 }
 
 template <bool COUNT, class Grid>
-__global__ void __launch_bounds__(256) shade_kernel(Grid g, const __grid_constant__ FrameParams f,
+__global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_constant__ FrameParams f,
                                                     TileMap m, Outputs o) {
     __shared__ float4 s_light[16];          // compacted active lights (slot order preserved)
     __shared__ int s_slot[16];
