@@ -71,7 +71,7 @@ struct vxrt_ctx {
     bool use_tile_order = true;
     bool use_culling = true;
     int l2_prefetch = 2;                // vxrt_set_l2_prefetch: 0 off, 1 on, 2 auto (on when this context renders <= 12,000 tiles)
-    int shade_threads = 256;            // threads per shade block (VXRT_SHADE_THREADS: 64 / 128 / 256)
+    int shade_threads = 128;            // threads per shade block (VXRT_SHADE_THREADS: 64 / 128 / 256; 128 measured best)
     int32_t* d_dbg_hit = nullptr;
     uint16_t* d_dbg_steps = nullptr;
     uint32_t* d_dbg_occl = nullptr;
