@@ -37,7 +37,10 @@ struct vxrt_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;         // device->host read-back of finished bands, overlapped with rendering
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_band[MAX_BANDS] = {};
+    cudaEvent_t ev_band[MAX_BANDS] = {};        // end of band b's kernels (the band's read-back waits for it)
+    cudaEvent_t ev_band_start[MAX_BANDS] = {};
+    float band_ms[MAX_BANDS] = {};              // kernel time of each band in the last banded frame ...
+    int band_ms_n = 0;                          // ... rendered with this many bands (0: none yet)
     cudaEvent_t ev_copy = nullptr;
     int readback_bands = 2;
     // pipelined read-back (vxrt_submit_frame_host): second device frame + per-slot "copy finished" events
@@ -292,7 +295,8 @@ extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
     if (cudaMalloc(&c->d_vox, c->nvox * 4) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaMalloc(grid) failed"));
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaStreamCreate failed"));
-    for (auto& e : c->ev_band) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
+    for (auto& e : c->ev_band) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
+    for (auto& e : c->ev_band_start) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
     if (cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
     for (auto& e : c->ev_slot) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
     if (cudaMalloc(&c->d_counters, sizeof(Counters) * MAX_BANDS) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaMalloc(counters) failed"));
@@ -330,6 +334,7 @@ extern "C" void vxrt_destroy(vxrt_ctx* c) {
     if (c->h_first) cudaFreeHost(c->h_first);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_band) if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_band_start) if (e) cudaEventDestroy(e);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     for (auto& e : c->ev_slot) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -632,6 +637,7 @@ extern "C" int vxrt_resize(vxrt_ctx* c, int width, int height) {                
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));      // queued read-backs still read the buffers freed below
     c->cfg.width = width; c->cfg.height = height;
+    c->band_ms_n = 0;
     c->frame.aspect = (float)width / height;
     return alloc_frame_buffers(c);
 }
@@ -682,7 +688,17 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         CUDA_TRY(cudaGetLastError());
         c->launches++;
     }
-    for (int b = 0; b < nbands; b++) {
+    // Banded read-back: the copy of a band overlaps the kernels of the bands after it, so the frame is in host memory
+    // soonest when the cheapest bands render first (their copies hide behind the expensive ones) -- the order of the
+    // previous banded frame's kernel times; the sky half of a frame costs a twentieth of the ground half.
+    int band_seq[MAX_BANDS];
+    for (int b = 0; b < nbands; b++) band_seq[b] = b;
+    const bool timed_bands = host_dst != nullptr && nbands > 1;
+    if (timed_bands && c->band_ms_n == nbands)
+        std::stable_sort(band_seq, band_seq + nbands, [&](int a, int b) { return c->band_ms[a] < c->band_ms[b]; });
+    for (int bi = 0; bi < nbands; bi++) {
+        const int b = band_seq[bi];
+        if (timed_bands) CUDA_TRY(cudaEventRecord(c->ev_band_start[b], c->stream));
         const int u0 = (int)((long long)units * b / nbands), u1 = (int)((long long)units * (b + 1) / nbands);
         const int tile0 = u0 * tiles_per_unit, ntile = (u1 - u0) * tiles_per_unit;
         if (ntile <= 0) continue;
@@ -831,6 +847,11 @@ extern "C" int vxrt_render_frame_host(vxrt_ctx* c, const vxrt_frame* f, uint8_t*
     if (rc != VXRT_OK) return rc;
     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->bands_used > 1) {                               // this frame's band times order the next frame's bands
+        for (int b = 0; b < c->bands_used; b++)
+            if (cudaEventElapsedTime(&c->band_ms[b], c->ev_band_start[b], c->ev_band[b]) != cudaSuccess) { cudaGetLastError(); c->band_ms[b] = 0.0f; }
+        c->band_ms_n = c->bands_used;
+    }
     if (!pinned) memcpy(out, c->h_frame, c->out_pixels * 4);
     return VXRT_OK;
 }
