@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: 'p2p' = kernels store straight into rank 0's frame over NVLink (no collective); "
                          "'nccl' = all-gather of tile buffers + un-tile kernel")
+    ap.add_argument("--e2e-path", default="auto", choices=["auto", "p2p", "host"],
+                    help="N > 1, how the frame reaches rank 0's host memory: p2p = peer stores over NVLink + one read-back on rank 0; "
+                         "host = every rank's kernels store into one shared page-locked host frame (auto: host from 4 GPUs on)")
     ap.add_argument("--bands", type=int, default=2, help="read-back bands of vxrt_render_frame_host (e2e, N = 1)")
     ap.add_argument("--no-cull", action="store_true", help="disable the occupancy-summary culling of certain misses (vxrt_set_culling)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads / cpu baseline (profiling runs)")
@@ -331,6 +334,70 @@ def run_b200(args):
         t0 = time.perf_counter()
         step_e2e()
         e2e_sync_s += time.perf_counter() - t0
+    # (c) N > 1, frames straight to host memory: no exchange at all -- the kernels of every rank store their tiles' pixels
+    # into ONE raster in shared page-locked host memory, each GPU over its own PCIe link; two host frames alternate and
+    # rank 0 takes frame k (completion flags of all ranks) while frame k + 1 renders.  Returns False (and the caller
+    # falls back to the peer-memory path) if the shared mapping cannot be set up on this box.
+    e2e_state = {}
+
+    def host_frame_e2e():
+        names = ["/vxrt_bench_%s_%d" % (os.environ.get("MASTER_PORT", "0"), i) for i in range(2)]
+        hfs, ok = [], True
+        try:
+            if rank == 0:
+                hfs = [vx.HostFrame(n, W, H, create=True) for n in names]
+        except vx.VxrtError as e:
+            print("host frames unavailable on rank 0: %s" % e, file=sys.stderr)
+            ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1 and rank != 0:
+            try:
+                hfs = [vx.HostFrame(n, W, H, create=False) for n in names]
+            except vx.VxrtError as e:
+                print("host frames unavailable on rank %d: %s" % (rank, e), file=sys.stderr)
+                ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            for h in hfs:
+                h.close()
+            return False
+        seq = [0, 0]
+
+        def run(nframes, flush):
+            """queue nframes; rank 0 takes each frame as soon as every rank delivered it (while the next one renders)"""
+            pending = None
+            for k in range(nframes):
+                if flush:
+                    flush_l2()
+                b = k & 1
+                seq[b] += 1
+                ren.renderToHostFrame(frame, hfs[b], seq[b])
+                if rank == 0 and pending is not None:
+                    hfs[pending[0]].wait(world, pending[1]); hfs[pending[0]].release(pending[1])
+                pending = (b, seq[b])
+            if rank == 0 and pending is not None:
+                hfs[pending[0]].wait(world, pending[1]); hfs[pending[0]].release(pending[1])
+            ren.sync()
+        run(4, False)
+        if rank == 0:                                                 # the frame that arrived is the frame
+            check = np.array(hfs[1].pixels(), copy=True)
+        barrier()
+        flush_l2(); ren.sync()
+        t0 = time.perf_counter()
+        run(args.steps, True)
+        e2e_state["s"] = time.perf_counter() - t0
+        barrier()
+        # the frame that arrived in the shared host frame == the frame the exchange path delivered (sync loop above)
+        e2e_state["frame_check"] = bool(np.array_equal(check, final_host.numpy())) if rank == 0 else True
+        e2e_state["api"] = ("every rank: vxrt_render_to_host_frame (host frame params in; its kernels store its tiles' pixels straight into one "
+                            "shared page-locked host frame over its own PCIe link, no exchange); rank 0: vxrt_host_frame_wait on every rank's "
+                            "completion flag, overlapped with the next frame (two host frames alternate); wall clock / K, max over ranks")
+        for h in hfs:
+            h.close()
+        return True
+
     # (b) pipelined (N = 1): the same call in its queued form -- every step still passes its frame parameters in and
     # gets its RGBA8 frame out to host memory, but the read-back of frame k overlaps the kernels of frame k+1
     if world == 1 and edits is None:
@@ -346,6 +413,8 @@ def run_b200(args):
         ren.waitFrames()
         e2e_s = time.perf_counter() - t0
         e2e_api = "vxrt_submit_frame_host x K + vxrt_wait_frames (C ABI): host frame params in, host RGBA8 frame out every step, read-back of frame k overlapped with the kernels of frame k+1; wall clock / K (includes the L2 flush kernels)"
+    elif world > 1 and edits is None and (args.e2e_path == "host" or (args.e2e_path == "auto" and world >= 4)) and host_frame_e2e():
+        e2e_s, e2e_api = e2e_state["s"], e2e_state["api"]
     elif use_p2p and edits is None:
         host_bufs = [ren.hostFrameBuffer(full_frame=True), ren.hostFrameBuffer(full_frame=True)] if rank == 0 else None
 
@@ -451,7 +520,8 @@ def run_b200(args):
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api,
                     "sync_ms_per_step": round(e2e_sync_s / args.steps * 1e3, 4),
-                    "sync_note": "vxrt_render_frame_host, one frame at a time (latency figure)"},
+                    "sync_note": "vxrt_render_frame_host, one frame at a time (latency figure)",
+                    **({"frame_check": e2e_state["frame_check"]} if "frame_check" in e2e_state else {})},
             "gpu_launches": int(args.steps * (st["kernel_launches"] + ((2 if use_p2p else 1) if world > 1 else 0))),
             "roofline": roofline,
             "wall_s_timed_region": round(t_wall, 3),

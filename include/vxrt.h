@@ -229,6 +229,27 @@ int vxrt_p2p_release_frame(vxrt_ctx* ctx);
 int vxrt_p2p_readback(vxrt_ctx* ctx, uint8_t* out);
 int vxrt_p2p_error(vxrt_ctx* ctx);
 
+/* ---- frames straight to host memory, any number of GPUs, no exchange ---------------------------
+   When the consumer of the frame is the HOST (a glReadPixels after the draw, an encoder, a file), the ranks need not
+   send their pixels to one GPU first: a host frame is ONE raster in page-locked host memory (POSIX shared memory,
+   registered with CUDA by every process that opens it) and the render kernels of every rank store their own tiles'
+   pixels straight into it, each GPU over its own PCIe link.
+     display rank : vxrt_host_frame_create(name, w, h, &hf)        other ranks : vxrt_host_frame_open(name, w, h, &hf)
+     every rank   : vxrt_render_to_host_frame(ctx, &frame, hf, seq)   (seq = 1, 2, 3, ...; returns when queued)
+     display rank : vxrt_host_frame_wait(hf, world, seq, timeout_ms) -> vxrt_host_frame_pixels(hf) holds frame seq
+                    ... consume ...   vxrt_host_frame_release(hf, seq)
+   Alternate between two host frames to overlap the consumption of one frame with the rendering of the next;
+   render_to_host_frame(seq) first waits (host side, bounded) until the display rank released frame seq - 1 of the
+   same host frame.  The completion flags live behind the pixels in the same shared mapping. */
+typedef struct vxrt_host_frame vxrt_host_frame;
+int vxrt_host_frame_create(const char* name, int width, int height, vxrt_host_frame** out);
+int vxrt_host_frame_open(const char* name, int width, int height, vxrt_host_frame** out);
+uint8_t* vxrt_host_frame_pixels(vxrt_host_frame* hf);
+int vxrt_render_to_host_frame(vxrt_ctx* ctx, const vxrt_frame* frame, vxrt_host_frame* hf, uint64_t seq);
+int vxrt_host_frame_wait(vxrt_host_frame* hf, int world, uint64_t seq, int timeout_ms);
+int vxrt_host_frame_release(vxrt_host_frame* hf, uint64_t seq);
+void vxrt_host_frame_destroy(vxrt_host_frame* hf);
+
 #ifdef __cplusplus
 }
 #endif

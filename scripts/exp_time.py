@@ -19,6 +19,7 @@ ap.add_argument("--prefetch", type=int, default=2)
 ap.add_argument("--no-flush", action="store_true")
 ap.add_argument("--no-order", action="store_true")
 ap.add_argument("--e2e", action="store_true", help="also sweep the read-back band count of the end-to-end call")
+ap.add_argument("--gaps", action="store_true", help="back-to-back frames: wall clock per frame against the kernels' own time (launch / sync overhead)")
 a = ap.parse_args()
 W0, H0 = 3840, 2160
 ren = vx.Renderer(grid=vx.scenes.DEFAULT_GRID, width=W0, height=H0, rank=0, world=a.world)
@@ -50,8 +51,36 @@ for wl in a.workloads.split(","):
         p.append(x["ms_primary"]); s.append(x["ms_shadow"]); t.append(x["ms_total"])
     m = statistics.mean(t)
     print("%-14s primary %.4f  shade %.4f  total %.4f ms  (min %.4f)  %.1f Mrays/s" % (wl, statistics.mean(p), statistics.mean(s), m, min(t), rays / m / 1e3))
-# end-to-end (host frame params in, host RGBA8 out) vs read-back band count, 4K / 16 lights
 import time
+if a.gaps:
+    # launch overhead: N frames queued back to back (no flush, no read-back) and the pipelined host call, wall clock
+    # per frame against the device time of one frame's kernels
+    fr = vx.scenes.frame_for("C3ii", ren.width, ren.height)
+    ren.updateUniforms(fr)
+    for _ in range(20):
+        ren.draw()
+    ren.sync()
+    N = 400
+    t0 = time.perf_counter()
+    for _ in range(N):
+        ren.draw()
+    t_queue = time.perf_counter() - t0
+    ren.sync()
+    t_all = time.perf_counter() - t0
+    k = ren.stats()["ms_total"]
+    print("gaps: vxrt_render x%d  host queueing %.4f ms/frame  wall %.4f ms/frame  kernels (events, last frame) %.4f ms" % (N, 1e3 * t_queue / N, 1e3 * t_all / N, k))
+    bufs = [ren.hostFrameBuffer(), ren.hostFrameBuffer()]
+    for i in range(8):
+        ren.submitFrameHost(fr, bufs[i & 1])
+    ren.waitFrames()
+    t0 = time.perf_counter()
+    for i in range(N):
+        ren.submitFrameHost(fr, bufs[i & 1])
+    t_queue = time.perf_counter() - t0
+    ren.waitFrames()
+    t_all = time.perf_counter() - t0
+    print("gaps: vxrt_submit_frame_host x%d  host queueing %.4f ms/frame  wall %.4f ms/frame" % (N, 1e3 * t_queue / N, 1e3 * t_all / N))
+# end-to-end (host frame params in, host RGBA8 out) vs read-back band count, 4K / 16 lights
 W, H = vx.scenes.RESOLUTIONS["4k"]
 if (W, H) != (ren.width, ren.height):
     ren.reshape(W, H)

@@ -98,6 +98,29 @@ def main():
     ren2.waitFrames()
     dist.barrier()
     readback_ok = bool(np.array_equal(bufs[0], got_edit_p2p) and np.array_equal(bufs[1], got_edit_p2p)) if rank == 0 else True
+    # frames straight to host memory: every rank's kernels store into one shared page-locked raster (no exchange)
+    names = ["/vxrt_mgc_%s_%d" % (os.environ.get("MASTER_PORT", "0"), i) for i in range(2)]
+    if rank == 0:
+        hfs = [vx.HostFrame(n, W, H, create=True) for n in names]
+    dist.barrier()
+    if rank != 0:
+        hfs = [vx.HostFrame(n, W, H, create=False) for n in names]
+    host_ok = True
+    for k in range(6):
+        ren.renderToHostFrame(frame, hfs[k & 1], k // 2 + 1)
+        if rank == 0 and k >= 1:
+            j = k - 1
+            hfs[j & 1].wait(world, j // 2 + 1)
+            host_ok &= bool(np.array_equal(hfs[j & 1].pixels(), got_edit))
+            hfs[j & 1].release(j // 2 + 1)
+    if rank == 0:
+        hfs[1].wait(world, 3)
+        host_ok &= bool(np.array_equal(hfs[1].pixels(), got_edit))
+        hfs[1].release(3)
+    ren.sync()
+    dist.barrier()
+    for h in hfs:
+        h.close()
     p2p_err = ren2.p2pError()
     fnv = vx.scenes.fnv1a64(ren.downloadGrid())
     fnvs = [None] * world
@@ -124,6 +147,8 @@ def main():
         print("peer-memory frame after edits vs oracle:", np.array_equal(got_edit_p2p, want2), "p2p_err", p2p_err)
         ok &= readback_ok
         print("pipelined peer-memory read-back frames intact:", readback_ok)
+        ok &= host_ok
+        print("frames stored straight into the shared host frame vs gathered frame:", host_ok)
         ok &= all(f == o.fnv(level) for f in fnvs)
         print("replica fingerprints equal oracle:", all(f == o.fnv(level) for f in fnvs), ["%016x" % f for f in fnvs])
     dist.barrier()

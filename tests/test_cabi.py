@@ -60,6 +60,19 @@ def test_no_gpu_means_loud_failure(vx):
         vx.Renderer()
 
 
+def test_host_frame_needs_a_device_and_leaves_nothing_behind(vx):
+    """the shared host frame is page-locked through CUDA: without a device its creation fails loudly and unlinks the name"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    name = "/vxrt_cabi_%d" % os.getpid()
+    with pytest.raises(vx.VxrtError, match="cudaHostRegister"):
+        vx.HostFrame(name, 64, 32, create=True)
+    assert not os.path.exists("/dev/shm" + name)
+    with pytest.raises(vx.VxrtError, match="shm_open"):
+        vx.HostFrame(name, 64, 32, create=False)
+
+
 def test_frame_struct_layout(vx):
     import ctypes as C
     import oracle_lib as ol

@@ -100,6 +100,13 @@ _SIGNATURES = {
     "vxrt_p2p_release_frame": (C.c_int, [C.c_void_p]),
     "vxrt_p2p_readback": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vxrt_p2p_error": (C.c_int, [C.c_void_p]),
+    "vxrt_host_frame_create": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "vxrt_host_frame_open": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "vxrt_host_frame_pixels": (C.c_void_p, [C.c_void_p]),
+    "vxrt_render_to_host_frame": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p, C.c_uint64]),
+    "vxrt_host_frame_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_int]),
+    "vxrt_host_frame_release": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "vxrt_host_frame_destroy": (None, [C.c_void_p]),
     "vxrt_assemble_tiles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
@@ -123,6 +130,40 @@ def load_library(build_if_missing=True):
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+class HostFrame:
+    """One raster RGBA8 frame in page-locked POSIX shared memory that the kernels of every rank store into
+    (include/vxrt.h: vxrt_host_frame_*).  create=True on the display rank, False on the ranks that open it."""
+
+    def __init__(self, name, width, height, create):
+        self.lib = load_library()
+        h = C.c_void_p()
+        fn = self.lib.vxrt_host_frame_create if create else self.lib.vxrt_host_frame_open
+        rc = fn(name.encode(), int(width), int(height), C.byref(h))
+        if rc != 0:
+            raise VxrtError("vxrt error %d: %s" % (rc, self.lib.vxrt_last_error().decode()))
+        self._h = h
+        self.width, self.height = int(width), int(height)
+
+    def pixels(self):
+        """[H][W][4] uint8 view of the shared frame, row 0 = bottom"""
+        p = self.lib.vxrt_host_frame_pixels(self._h)
+        buf = (C.c_uint8 * (self.width * self.height * 4)).from_address(p)
+        return np.frombuffer(buf, np.uint8).reshape(self.height, self.width, 4)
+
+    def wait(self, world, seq, timeout_ms=4000):
+        rc = self.lib.vxrt_host_frame_wait(self._h, int(world), C.c_uint64(seq), int(timeout_ms))
+        if rc != 0:
+            raise VxrtError("vxrt error %d: %s" % (rc, self.lib.vxrt_last_error().decode()))
+
+    def release(self, seq):
+        self.lib.vxrt_host_frame_release(self._h, C.c_uint64(seq))
+
+    def close(self):
+        if self._h:
+            self.lib.vxrt_host_frame_destroy(self._h)
+            self._h = None
 
 
 def make_frame(cam_pos, rotate=None, light_pos=(256.0, 1536.0, 256.0), aspect=16.0 / 9.0, view=0, lights=None,
@@ -421,6 +462,10 @@ class Renderer:
 
     def p2pError(self):
         return self._check(self.lib.vxrt_p2p_error(self._h))
+
+    def renderToHostFrame(self, frame, host_frame, seq):
+        """queue this rank's kernels; they store its tiles' pixels straight into the shared host frame"""
+        self._check(self.lib.vxrt_render_to_host_frame(self._h, C.byref(frame), host_frame._h, C.c_uint64(seq)))
 
     def assembleTiles(self, gathered_ptr, dst_ptr, stream_ptr=0):
         self._check(self.lib.vxrt_assemble_tiles(self._h, C.c_void_p(gathered_ptr), C.c_void_p(dst_ptr), C.c_void_p(stream_ptr)))

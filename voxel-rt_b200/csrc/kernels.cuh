@@ -483,6 +483,13 @@ __global__ void p2p_release_kernel(P2PShared* sh, unsigned long long seq) {
 }
 
 // gathered: [world][nlocal][8][32] RGBA8 -> raster [height][width]
+// completion flag of a host frame: system-scope store after the stream's earlier kernels (posted writes of one device
+// stay ordered, so the host sees the pixels before the flag)
+__global__ void host_flag_kernel(unsigned long long* flag, unsigned long long seq) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(flag), "l"(seq) : "memory");
+}
+
 __global__ void assemble_kernel(const uint32_t* __restrict__ gathered, uint32_t* __restrict__ dst, TileMap m) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= m.width * m.height) return;

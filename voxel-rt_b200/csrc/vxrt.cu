@@ -5,6 +5,12 @@
 #include "kernels.cuh"
 
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <chrono>
+#include <thread>
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -645,7 +651,8 @@ extern "C" int vxrt_resize(vxrt_ctx* c, int width, int height) {                
 // Launches the frame's kernels in `nbands` bands of whole tile rows.  host_dst != nullptr: each band's pixels are
 // copied to host_dst (page-locked) on the copy stream as soon as the band's kernels finish, so the read-back of
 // band b overlaps the rendering of band b+1.
-static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* dev_out = nullptr, bool fence_main = true) {
+static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* dev_out = nullptr, bool fence_main = true, bool raster_out = false) {
+    const bool p2p_frame = c->p2p && !raster_out;         // a host-frame render of a peer-memory context leaves the peer frame alone
     if (!dev_out) dev_out = c->d_rgba8;
     if (fence_main)                                       // synchronous paths: never overwrite a frame a pipelined copy still reads
         for (int slot = 0; slot < 2; slot++)
@@ -669,7 +676,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
     c->launches = 0;
     c->bands_used = nbands;
     CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(Counters) * MAX_BANDS, c->stream));
-    if (c->p2p) {
+    if (p2p_frame) {
         if (host_dst) return fail(VXRT_ERR_STATE, "render_frame_host is not available on a peer-memory context: use vxrt_p2p_wait_frame on the owner");
         p2p_wait_consumed_kernel<<<1, 1, 0, c->stream>>>((const P2PShared*)c->p2p_base, c->p2p_seq, c->d_p2p_err);
         CUDA_TRY(cudaGetLastError());
@@ -705,8 +712,8 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         TileMap m = c->map;
         m.tile_base = tile0;
         Outputs o;
-        o.rgba8 = c->p2p ? (uint32_t*)(c->p2p_base + sizeof(P2PShared) + (c->p2p_seq & 1) * c->p2p_frame_bytes) : dev_out;
-        o.raster = (c->cfg.world == 1 || c->p2p) ? 1 : 0;
+        o.rgba8 = p2p_frame ? (uint32_t*)(c->p2p_base + sizeof(P2PShared) + (c->p2p_seq & 1) * c->p2p_frame_bytes) : dev_out;
+        o.raster = (c->cfg.world == 1 || p2p_frame || raster_out) ? 1 : 0;
         o.skip_dark = c->use_culling ? 1 : 0;
         o.hitq = c->d_hitq; o.hitpix = c->d_hitpix; o.tile_hits = c->d_tile_hits;
         o.counters = c->d_counters + b;
@@ -774,7 +781,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
     if (nbands != 1) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
     if (nbands == 1 && c->use_tile_order) c->order_frame++;
-    if (c->p2p) {
+    if (p2p_frame) {
         p2p_signal_done_kernel<<<1, 1, 0, c->stream>>>((P2PShared*)c->p2p_base, c->cfg.rank, c->p2p_seq);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
@@ -1123,6 +1130,110 @@ extern "C" int vxrt_p2p_error(vxrt_ctx* c) {
     CUDA_TRY(cudaMemcpyAsync(&e, c->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return e;
+}
+
+// ---- host frames ---------------------------------------------------------------------------------
+struct vxrt_host_frame {
+    uint8_t* base = nullptr;            // mapping: pixels, then (page-aligned) HostFrameFlags
+    size_t pixel_bytes = 0, total = 0;
+    int width = 0, height = 0;
+    bool owner = false, registered = false;
+    std::string name;
+};
+struct HostFrameFlags {
+    unsigned long long done[64];        // done[rank] = last frame whose pixels of that rank are in the mapping
+    unsigned long long released;        // last frame the display rank has finished with
+};
+
+static HostFrameFlags* host_frame_flags(vxrt_host_frame* hf) { return (HostFrameFlags*)(hf->base + hf->total - 4096); }
+
+static int host_frame_map(const char* name, int width, int height, bool create, vxrt_host_frame** out) {
+    if (!name || !out || width <= 0 || height <= 0) return fail(VXRT_ERR_INVALID, "host_frame: bad argument");
+    *out = nullptr;
+    const size_t pixel_bytes = (size_t)width * height * 4;
+    const size_t total = ((pixel_bytes + 4095) / 4096) * 4096 + 4096;
+    const int fd = shm_open(name, create ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
+    if (fd < 0) return fail(VXRT_ERR_IO, std::string("host_frame: shm_open failed for ") + name);
+    if (create && ftruncate(fd, (off_t)total) != 0) { close(fd); shm_unlink(name); return fail(VXRT_ERR_IO, "host_frame: ftruncate failed"); }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || (size_t)st.st_size != total) { close(fd); if (create) shm_unlink(name); return fail(VXRT_ERR_INVALID, "host_frame: the shared mapping has a different size (other extents?)"); }
+    void* p = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_POPULATE, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { if (create) shm_unlink(name); return fail(VXRT_ERR_IO, "host_frame: mmap failed"); }
+    if (create) memset(p, 0, total);
+    vxrt_host_frame* hf = new vxrt_host_frame();
+    hf->base = (uint8_t*)p; hf->pixel_bytes = pixel_bytes; hf->total = total; hf->width = width; hf->height = height;
+    hf->owner = create; hf->name = name;
+    const cudaError_t e = cudaHostRegister(p, total, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        munmap(p, total);
+        if (create) shm_unlink(name);
+        delete hf;
+        return fail(VXRT_ERR_CUDA, std::string("host_frame: cudaHostRegister: ") + cudaGetErrorString(e));
+    }
+    hf->registered = true;
+    *out = hf;
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_host_frame_create(const char* name, int width, int height, vxrt_host_frame** out) { return host_frame_map(name, width, height, true, out); }
+extern "C" int vxrt_host_frame_open(const char* name, int width, int height, vxrt_host_frame** out) { return host_frame_map(name, width, height, false, out); }
+extern "C" uint8_t* vxrt_host_frame_pixels(vxrt_host_frame* hf) { return hf ? hf->base : nullptr; }
+
+extern "C" void vxrt_host_frame_destroy(vxrt_host_frame* hf) {
+    if (!hf) return;
+    if (hf->registered) { cudaHostUnregister(hf->base); cudaGetLastError(); }
+    munmap(hf->base, hf->total);
+    if (hf->owner) shm_unlink(hf->name.c_str());
+    delete hf;
+}
+
+// bounded host-side spin on a flag in the shared mapping
+static bool host_spin_until(const volatile unsigned long long* flag, unsigned long long want, int timeout_ms) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spins = 0;; spins++) {
+        if (__atomic_load_n(flag, __ATOMIC_ACQUIRE) >= want) return true;
+        if ((spins & 1023u) == 1023u) {
+            if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() > timeout_ms) return false;
+            std::this_thread::yield();
+        }
+    }
+}
+
+extern "C" int vxrt_render_to_host_frame(vxrt_ctx* c, const vxrt_frame* f, vxrt_host_frame* hf, uint64_t seq) {
+    if (!hf || seq == 0) return fail(VXRT_ERR_INVALID, "render_to_host_frame: null host frame or seq 0");
+    int rc = vxrt_set_frame(c, f);
+    if (rc != VXRT_OK) return rc;
+    CHECK_CTX(c);
+    if (hf->width != c->cfg.width || hf->height != c->cfg.height) return fail(VXRT_ERR_INVALID, "render_to_host_frame: the host frame has other extents than the context");
+    if (c->cfg.rank >= 64) return fail(VXRT_ERR_INVALID, "render_to_host_frame: at most 64 ranks");
+    HostFrameFlags* fl = host_frame_flags(hf);
+    // the previous frame of THIS host frame must have been released by the display rank before it is overwritten
+    if (seq > 1 && !host_spin_until(&fl->released, seq - 1, 4000)) return fail(VXRT_ERR_STATE, "render_to_host_frame: the display rank did not release the previous frame (4 s)");
+    void* dpix = nullptr;
+    CUDA_TRY(cudaHostGetDevicePointer(&dpix, hf->base, 0));
+    rc = render_bands(c, 1, nullptr, (uint32_t*)dpix, /*fence_main=*/true, /*raster_out=*/true);
+    if (rc != VXRT_OK) return rc;
+    unsigned long long* dflag = (unsigned long long*)((uint8_t*)dpix + ((uint8_t*)&fl->done[c->cfg.rank] - hf->base));
+    host_flag_kernel<<<1, 1, 0, c->stream>>>(dflag, (unsigned long long)seq);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_host_frame_wait(vxrt_host_frame* hf, int world, uint64_t seq, int timeout_ms) {
+    if (!hf || world < 1 || world > 64) return fail(VXRT_ERR_INVALID, "host_frame_wait: bad argument");
+    HostFrameFlags* fl = host_frame_flags(hf);
+    for (int r = 0; r < world; r++)
+        if (!host_spin_until(&fl->done[r], seq, timeout_ms)) return fail(VXRT_ERR_STATE, "host_frame_wait: rank " + std::to_string(r) + " did not deliver the frame in time");
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_host_frame_release(vxrt_host_frame* hf, uint64_t seq) {
+    if (!hf) return fail(VXRT_ERR_INVALID, "host_frame_release: null host frame");
+    __atomic_store_n(&host_frame_flags(hf)->released, (unsigned long long)seq, __ATOMIC_RELEASE);
+    return VXRT_OK;
 }
 
 extern "C" int vxrt_assemble_tiles(vxrt_ctx* c, const void* gathered, void* dst, void* stream) {
