@@ -99,6 +99,12 @@ int vxrt_upload_range(vxrt_ctx* ctx, size_t first, size_t count, const int32_t* 
    *rows_out (optional) receives the number of rows uploaded (the reference's glBufferSubData call count). */
 int vxrt_update_partial(vxrt_ctx* ctx, const float start[3], const float end[3], const int32_t* host_voxels,
                         int32_t* rows_out);
+/* a batch of glBufferSubData calls of one length -- what ONE updatePartialGeometry issues (render.cpp:214-221: 900 calls
+   of 124 bytes per destruction) -- as one staged copy + scatter kernel: row r covers voxels [firsts[r], firsts[r]+row_len),
+   its data is packed[r*row_len ...] (copied at call time).  Rows of one batch must not overlap unless they carry the
+   same data.  Any row outside the buffer fails the whole call (GL_INVALID_VALUE), nothing is uploaded.  Used by the
+   link-level GL shim (voxel-rt_b200/csrc/host/vxrt_glshim.cpp). */
+int vxrt_upload_rows(vxrt_ctx* ctx, size_t rows, size_t row_len, const int64_t* firsts, const int32_t* packed);
 int vxrt_download_grid(vxrt_ctx* ctx, int32_t* out, size_t count);
 /* copy the device box [lo,hi) (clamped to the grid) into the caller's FULL-GRID array (host mirror sync after
    a device-side edit; the reference's CPU collision code reads voxels[], controls.cpp:10-19) */

@@ -104,3 +104,49 @@ def test_headless_saves_the_edited_level(vx, oracle, default_level, tmp_path):
     assert dims == gc.DIMS and np.array_equal(got, level)
     raw, _, _ = run_headless(vx, tmp_path, "--size", W, H, "--load", path)
     assert np.array_equal(np.fromfile(raw, np.uint8), first)
+
+
+# ---- the reference's own game on the B200 path (link-level seam) -------------------------------
+GAME = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "voxel_rt_on_vxrt")
+
+
+@pytest.mark.skipif(not os.path.exists(GAME), reason="oracle/_ref/voxel_rt_on_vxrt not built (make -C oracle ref)")
+@pytest.mark.skipif(os.environ.get("VXRT_TEST_GLSHIM_GPU") != "1",
+                    reason="written after round 1's GPU budget was spent: not run on a B200 yet; VXRT_TEST_GLSHIM_GPU=1 enables it "
+                           "(the same session against an oracle-backed mock libvxrt runs on the CPU: tests/test_glshim.py)")
+def test_reference_game_on_the_b200_through_the_gl_shim(vx, oracle, default_level, tmp_path):
+    """oracle/_ref/voxel_rt_on_vxrt = the reference's six objects, unmodified, linked against libvxrt_glshim.so + libvxrt.so:
+    its own main loop (main.cpp:47-75) with scripted input -- look down, place a light, right-click destruction (900
+    glBufferSubData calls -> one vxrt_upload_rows), window resize, walking.  Dumped frames and the final device grid
+    against the oracle, bit for bit."""
+    import test_glshim as tg
+    vx.build.build_glshim()
+    script = "1:mouse:400,600;1:lmb:down;9:lmb:up;10:key:T:down;11:key:T:up;12:rmb:down;13:rmb:up;15:resize:640x360;18:key:W:down"
+    r = tg.run_game(tg.shader_dir(tmp_path), {
+        "VXRT_GLSHIM_READY_UPLOADS": "2", "VXRT_GLSHIM_FRAMES": "24", "VXRT_GLSHIM_FPS": "60", "VXRT_GLSHIM_EVENTS": script,
+        "VXRT_GLSHIM_DUMP": str(tmp_path / "f%02d.ppm"), "VXRT_GLSHIM_DUMP_FRAMES": "11,12,14,20", "VXRT_GLSHIM_LOG": "1",
+        "VXRT_GLSHIM_SAVE_GRID": str(tmp_path / "final.vxg")})
+    assert r.returncode == 0, r.stderr
+    assert "24 frames at 640x360" in r.stderr and "900 glBufferSubData calls in 1 batches" in r.stderr
+
+    def dumped(n, w, h):
+        data = (tmp_path / ("f%02d.ppm" % n)).read_bytes()
+        head = b"P6\n%d %d\n255\n" % (w, h)
+        assert data.startswith(head) and len(data) == len(head) + w * h * 3
+        fr = ol.Frame.from_buffer_copy((tmp_path / ("f%02d.ppm.frame" % n)).read_bytes())
+        return np.frombuffer(data[len(head):], np.uint8).reshape(h, w, 3), fr
+
+    # frames 11 and 12 precede the edit: the reference level with its depth field, the camera at rest looking down
+    img11, fr11 = dumped(11, 800, 600)
+    img12, fr12 = dumped(12, 800, 600)
+    assert list(fr11.cam_pos) == list(fr12.cam_pos) and list(fr11.rotate) == list(fr12.rotate)
+    assert np.array_equal(img11, oracle.render(default_level, gc.DIMS, fr11, 800, 600)["rgba8"][::-1, :, :3])
+    # doDestroy (controls.cpp:100-110) used camPos and camDir = rotateMatrix * (0,0,1,1) = the matrix's third column
+    edited = default_level.copy()
+    oracle.do_destroy(edited, gc.DIMS, np.array(fr12.cam_pos, np.float32), np.array(fr12.rotate[8:11], np.float32))
+    assert not np.array_equal(edited, default_level)
+    saved, dims = vx.gridfile.read_grid(str(tmp_path / "final.vxg"))
+    assert dims == gc.DIMS and np.array_equal(saved, edited)
+    for n, (w, h) in ((14, (800, 600)), (20, (640, 360))):
+        img, fr = dumped(n, w, h)
+        assert np.array_equal(img, oracle.render(edited, gc.DIMS, fr, w, h)["rgba8"][::-1, :, :3])

@@ -357,6 +357,32 @@ def test_upload_download_round_trip_and_ranges(vx, oracle, default_level):
             r.updateGeometry(host[:-1])
 
 
+def test_upload_rows_is_a_batch_of_sub_data_calls(vx, oracle, default_level):
+    """vxrt_upload_rows == the 900 equally long glBufferSubData calls of one updatePartialGeometry (render.cpp:214-221),
+    incl. rows that run past x = 511 into the next row; a row outside the buffer fails the whole batch"""
+    host = default_level.copy()
+    with vx.Renderer(grid=gc.DIMS, width=32, height=8) as r:
+        r.updateGeometry(host)
+        edited = host.copy()
+        oracle.remove_sphere(edited, gc.DIMS, 195, 40, 155, 7)
+        oracle.remove_sphere(edited, gc.DIMS, 505, 40, 155, 7)
+        dev = host.copy()
+        first, count, n = oracle.partial_ranges(gc.DIMS, (180.0, 25.0, 140.0), (210.0, 55.0, 170.0))
+        assert n == 900 and set(count.tolist()) == {31}
+        wrapping = np.array([500 + 512 * (y + 96 * z) for z in range(148, 163) for y in range(33, 48)], np.int64)
+        for firsts, length in ((first, 31), (wrapping, 31)):       # the second batch runs past x = 511 into the next row
+            rows = np.stack([edited[f:f + length] for f in firsts])
+            r.uploadRows(firsts, rows)
+            for f in firsts:
+                dev[f:f + length] = edited[f:f + length]
+            assert np.array_equal(r.downloadGrid(), dev)
+        assert not np.array_equal(dev, host)
+        with pytest.raises(vx.VxrtError):
+            r.uploadRows([0, host.size - 3], np.zeros((2, 8), np.int32))
+        assert np.array_equal(r.downloadGrid(), dev)
+        r.uploadRows(np.zeros(0, np.int64), np.zeros((0, 8), np.int32))      # empty batch: nothing happens
+
+
 def test_device_depth_field_builder_matches_reference_fingerprint(vx, oracle, golden):
     nodepth = oracle.default_level(depth_field=False)
     with vx.Renderer(grid=gc.DIMS, width=32, height=8) as r:

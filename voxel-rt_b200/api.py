@@ -55,6 +55,7 @@ _SIGNATURES = {
     "vxrt_fnv1a64": (C.c_uint64, [C.c_void_p, C.c_size_t]),
     "vxrt_upload_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "vxrt_upload_range": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "vxrt_upload_rows": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
     "vxrt_update_partial": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.POINTER(C.c_int32)]),
     "vxrt_download_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "vxrt_download_box": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]),
@@ -248,6 +249,14 @@ class Renderer:
         """one glBufferSubData (render.cpp:219)."""
         s = np.ascontiguousarray(src, np.int32).ravel()
         self._check(self.lib.vxrt_upload_range(self._h, int(first), s.size, _vp(s)))
+
+    def uploadRows(self, firsts, rows):
+        """a batch of equally long glBufferSubData calls (render.cpp:214-221) as one staged copy + scatter kernel;
+        rows: [n][row_len] int32, firsts: [n] first voxel index of each row."""
+        r = np.ascontiguousarray(rows, np.int32)
+        f = np.ascontiguousarray(firsts, np.int64).ravel()
+        assert r.ndim == 2 and r.shape[0] == f.size
+        self._check(self.lib.vxrt_upload_rows(self._h, r.shape[0], r.shape[1], _vp(f), _vp(r)))
 
     def updatePartialGeometry(self, start, end, host_voxels):
         """render.cpp:204-223; returns the number of rows uploaded."""

@@ -50,6 +50,24 @@ def build_host(force=False):
     return HEADLESS
 
 
+GLSHIM_SRC = os.path.join(HERE, "csrc", "host", "vxrt_glshim.cpp")
+GLSHIM = os.path.join(HERE, "libvxrt_glshim.so")
+
+
+def build_glshim(force=False):
+    """the link-level seam: the GL / GLEW / GLFW symbols the reference's objects import, forwarded to libvxrt.so"""
+    deps = [GLSHIM_SRC, os.path.join(os.path.dirname(HERE), "include", "vxrt.h"), LIB]
+    if not force and os.path.exists(GLSHIM) and all(os.path.getmtime(d) <= os.path.getmtime(GLSHIM) for d in deps):
+        return GLSHIM
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-fPIC", "-shared", "-o", GLSHIM, GLSHIM_SRC,
+           "-L" + HERE, "-lvxrt", "-ldl", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building libvxrt_glshim.so")
+    return GLSHIM
+
+
 def lib_path():
     """VXRT_LIB overrides the in-tree library (kernel experiments: scripts/exp_time.py)"""
     return os.environ.get("VXRT_LIB", LIB)
@@ -82,3 +100,4 @@ if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_host(force="--force" in sys.argv))
     print(build_hostlogic(force="--force" in sys.argv))
+    print(build_glshim(force="--force" in sys.argv))

@@ -367,6 +367,25 @@ extern "C" int vxrt_upload_range(vxrt_ctx* c, size_t first, size_t count, const 
     return update_yrange(c, first, count, false);
 }
 
+// rows of `row_len` voxels staged back to back in h_stage, their first grid indices in h_first: one copy of each to the
+// device, one scatter kernel (one block per row), then the occupancy summary takes in any new solids
+static int scatter_staged_rows(vxrt_ctx* c, size_t rows, int row_len) {
+    const size_t elems = rows * (size_t)row_len;
+    CUDA_TRY(cudaMemcpyAsync(c->d_stage, c->h_stage, elems * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_first, c->h_first, rows * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    scatter_rows_kernel<<<(unsigned)rows, 64, 0, c->stream>>>(c->d_vox, c->d_stage, c->d_first, row_len);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));      // staging buffers are reused by the next call
+    for (size_t r = 0; r < rows; r++)                 // rows uploaded may hold new solids
+        for (int i = 0; i < row_len; i++)
+            if (c->h_stage[r * (size_t)row_len + i] >= 0) {
+                const int y = (int)(((c->h_first[r] + i) / c->cfg.grid_w) % c->cfg.grid_h);
+                if (y < c->yrange[0]) c->yrange[0] = y;
+                if (y > c->yrange[1]) c->yrange[1] = y;
+            }
+    return VXRT_OK;
+}
+
 // updatePartialGeometry(start,end) render.cpp:204-223 -- same (int) casts, same float loop counters, same
 // start/end swap on linear indices, same "skip the row when its first index is out of bounds".
 extern "C" int vxrt_update_partial(vxrt_ctx* c, const float start_in[3], const float end_in[3],
@@ -386,26 +405,31 @@ extern "C" int vxrt_update_partial(vxrt_ctx* c, const float start_in[3], const f
         }
     if (rows_out) *rows_out = (int32_t)firsts.size();
     if (firsts.empty()) return VXRT_OK;
-    const size_t rows = firsts.size(), elems = rows * (size_t)xLength;
-    int rc = ensure_stage(c, elems, rows);
+    const size_t rows = firsts.size();
+    int rc = ensure_stage(c, rows * (size_t)xLength, rows);
     if (rc != VXRT_OK) return rc;
     for (size_t r = 0; r < rows; r++) {
         memcpy(c->h_stage + r * xLength, host_voxels + firsts[r], (size_t)xLength * 4);
         c->h_first[r] = firsts[r];
     }
-    CUDA_TRY(cudaMemcpyAsync(c->d_stage, c->h_stage, elems * 4, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->d_first, c->h_first, rows * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
-    scatter_rows_kernel<<<(unsigned)rows, 64, 0, c->stream>>>(c->d_vox, c->d_stage, c->d_first, xLength);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(c->stream));      // staging buffers are reused by the next call
-    for (size_t r = 0; r < rows; r++)                 // rows uploaded may hold new solids
-        for (int i = 0; i < xLength; i++)
-            if (host_voxels[firsts[r] + i] >= 0) {
-                const int y = (int)(((firsts[r] + i) / c->cfg.grid_w) % c->cfg.grid_h);
-                if (y < c->yrange[0]) c->yrange[0] = y;
-                if (y > c->yrange[1]) c->yrange[1] = y;
-            }
-    return VXRT_OK;
+    return scatter_staged_rows(c, rows, xLength);
+}
+
+// A batch of glBufferSubData calls of one length (what one updatePartialGeometry issues, render.cpp:214-221) as ONE
+// staged copy + scatter kernel; packed holds the rows back to back, copied at call time like GL does.
+extern "C" int vxrt_upload_rows(vxrt_ctx* c, size_t rows, size_t row_len, const int64_t* firsts, const int32_t* packed) {
+    CHECK_CTX(c);
+    if (rows == 0 || row_len == 0) return VXRT_OK;
+    if (!firsts || !packed) return fail(VXRT_ERR_INVALID, "upload_rows: null argument");
+    if (row_len > (size_t)INT_MAX || rows > (size_t)INT_MAX) return fail(VXRT_ERR_INVALID, "upload_rows: too many / too long rows");
+    for (size_t r = 0; r < rows; r++)
+        if (firsts[r] < 0 || (size_t)firsts[r] > c->nvox || row_len > c->nvox - (size_t)firsts[r])
+            return fail(VXRT_ERR_INVALID, "upload_rows: row outside the buffer (GL_INVALID_VALUE)");
+    int rc = ensure_stage(c, rows * row_len, rows);
+    if (rc != VXRT_OK) return rc;
+    memcpy(c->h_stage, packed, rows * row_len * 4);
+    for (size_t r = 0; r < rows; r++) c->h_first[r] = firsts[r];
+    return scatter_staged_rows(c, rows, (int)row_len);
 }
 
 extern "C" int vxrt_download_grid(vxrt_ctx* c, int32_t* out, size_t count) {
