@@ -113,6 +113,26 @@ void vxo_shade_pixel(const int32_t* vox, vxo_dims g, const vxo_frame* f, int wid
 
 int vxo_num_threads(void);
 
+/* ---- analysis only (scripts/where_iterations_go.py; not part of the restatement) ----------------------------
+ * cell[kind][outcome]: kind 0 primary / 1 global-light / 2 local-light ray; outcome 0 hit / 1 left the grid /
+ * 2 budget exhausted.  "after_cull": iterations that came after the ray's cell first lay beyond every grid row holding
+ * a solid, in its direction of travel (the CUDA path's occupancy-summary culling ends the ray there).  "dark": rays
+ * from a surface that faces away from their light (N.L <= 0; the CUDA path does not trace them). */
+typedef struct {
+    uint64_t rays, iterations, jumps;
+    uint64_t rays_culled, iterations_after_cull;
+    uint64_t rays_dark, iterations_dark, iterations_dark_after_cull;
+} vxo_profile_cell;
+#define VXO_BOX_VARIANTS 8           /* clear-box test: (boxes along the ray, x/z granularity of the table), see vxo.c */
+typedef struct { uint64_t rays, iterations, violations; } vxo_profile_box;   /* lit shadow / light rays whose box is clear */
+typedef struct {
+    vxo_profile_cell cell[3][3];
+    vxo_profile_box box[3][VXO_BOX_VARIANTS];
+    uint64_t longest[3];            /* most iterations of a single ray, per kind */
+    int32_t ymin, ymax;             /* rows that hold a solid voxel */
+} vxo_profile;
+void vxo_profile_frame(const int32_t* vox, vxo_dims g, const vxo_frame* f, int width, int height, vxo_profile* out);
+
 #ifdef __cplusplus
 }
 #endif
