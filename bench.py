@@ -11,6 +11,7 @@ the frame.  Rays are counted by the REFERENCE's casting rule: W*H
 ray per hit pixel, one local-light ray per (hit pixel, light) the reference shader would cast.
 N > 1: sort-first image-tile split (tile t -> rank t % N), grid replicated, one NCCL all-gather of the RGBA8
 tiles per frame + an un-tile kernel on every rank; total work is fixed => "scaling": "strong".
+--partition frames (opt-in): whole frames are the sharded unit instead (frame f on rank f % N, nothing exchanged) => "weak".
 
 Prints ONE JSON line (rank 0).
 """
@@ -56,6 +57,10 @@ def parse():
     ap.add_argument("--e2e-path", default="auto", choices=["auto", "p2p", "host"],
                     help="N > 1, how the frame reaches rank 0's host memory: p2p = peer stores over NVLink + one read-back on rank 0; "
                          "host = every rank's kernels store into one shared page-locked host frame (auto: host from 4 GPUs on)")
+    ap.add_argument("--partition", default="tiles", choices=["tiles", "frames"],
+                    help="N > 1: 'tiles' (default, BASELINE's split) = every GPU renders its tiles of the SAME frame (strong scaling, "
+                         "shorter frame latency); 'frames' = every GPU renders whole frames of its own (frame f on rank f %% N, no "
+                         "exchange at all: weak scaling, N times the frame rate at single-GPU latency)")
     ap.add_argument("--bands", type=int, default=2, help="read-back bands of vxrt_render_frame_host (e2e, N = 1)")
     ap.add_argument("--no-cull", action="store_true", help="disable the occupancy-summary culling of certain misses (vxrt_set_culling)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads / cpu baseline (profiling runs)")
@@ -576,6 +581,130 @@ def extra_workloads(vx, ren, flush_l2, stream, torch, steps=10):
 
 
 # =====================================================================================================
+def run_frame_sharded(args):
+    """--partition frames (N > 1, opt-in): whole frames are the sharded unit.  Rank r renders frames r, r + N, r + 2N, ... of
+    the stream on its own replica of the grid and reads each back over its own PCIe link; nothing is exchanged between the
+    GPUs, so the frame rate scales with N while one frame still takes the single-GPU time.  A step = every rank renders one
+    frame (N frames per step): per-GPU work is fixed => "scaling": "weak".  Same kernels, same timing discipline as the
+    default tile split (run_b200); NOT yet run on a GPU box (written after round 1's GPU minutes were spent)."""
+    import torch
+    import torch.distributed as dist
+    import voxel_rt_b200 as vx
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus or world < 2:
+        raise SystemExit("--partition frames: launch with torch.distributed.run --nproc-per-node N (N = --gpus >= 2)")
+    scene, reskey = WORKLOADS[args.workload]
+    if scene in ("C4", "C5"):
+        raise SystemExit("--partition frames supports the default-level workloads only")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: libvxrt has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W, H = vx.scenes.RESOLUTIONS[reskey]
+    grid = vx.scenes.DEFAULT_GRID
+    frame = vx.scenes.frame_for(scene, W, H)
+    ren = vx.Renderer(grid=grid, width=W, height=H, device=local_rank)          # world = 1: this replica renders whole frames
+    ren.initVoxels()
+    ren.buildDepthField()
+    level_fnv = "%016x" % vx.scenes.fnv1a64(ren.downloadGrid())
+    assert level_fnv == "4c58cc4001a22afa", level_fnv
+    ren.setCulling(not args.no_cull)
+    stream = torch.cuda.ExternalStream(ren.stream_ptr(), device=torch.device("cuda", local_rank))
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ren.updateUniforms(frame)
+    for nwarm in range(max(args.warmup, 3) + 200):
+        flush_l2(); ren.draw()
+        if nwarm % 16 == 15:
+            ren.sync()
+    barrier()
+    st = ren.stats()
+    ren.setStats(False)
+    for _ in range(3):
+        flush_l2(); ren.draw()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = {"primary": [], "shade": []}
+    for k in range(args.steps):
+        flush_l2()
+        ev[k][0].record(stream)
+        ren.draw()
+        ev[k][1].record(stream)
+        if k % 8 == 7 or k == args.steps - 1:
+            ren.sync()
+            s = ren.stats(); kern_ms["primary"].append(s["ms_primary"]); kern_ms["shade"].append(s["ms_shadow"])
+    barrier()
+    total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    # e2e: every rank pipelines its own frames to its own page-locked buffers (vxrt_submit_frame_host)
+    host_bufs = [ren.hostFrameBuffer(), ren.hostFrameBuffer()]
+    for k in range(4):
+        ren.submitFrameHost(frame, host_bufs[k & 1])
+    ren.waitFrames()
+    barrier()
+    flush_l2(); ren.sync()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        flush_l2()
+        ren.submitFrameHost(frame, host_bufs[k & 1])
+    ren.waitFrames()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = (float(x) for x in t.tolist())
+    clocks = sampler.stop()
+    rays = vx.scenes.total_rays(st)                                # per frame; every rank renders the same benchmark frame
+    ms_per_step = total_ms / args.steps                            # one step = N frames, one per rank
+    result = None
+    if rank == 0:
+        hbm, peak_src = peaks()
+        prim_ms, shade_ms = statistics.mean(kern_ms["primary"]), statistics.mean(kern_ms["shade"])
+        fs = st["fetches"] - st["fetches_primary"]
+        bytes_shade = 4 * fs + 8 * st["hit_pixels"]
+        achieved = bytes_shade / (shade_ms * 1e-3) / 1e9 if shade_ms > 0 else 0.0
+        result = {
+            "metric": METRIC, "value": round(world * rays / (ms_per_step * 1e-3) / 1e6, 2), "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (reference procedural default level, fnv1a64 %s; fixed camera)" % level_fnv,
+            "config": {"workload": args.workload, "grid": list(grid), "width": W, "height": H, "local_lights": 16 if scene != "C1" else 0,
+                       "rays_per_frame": rays, "frames_per_step": world, "voxel_fetches_per_frame": st["fetches"],
+                       "partition": "frame-sharded: rank r renders whole frames r, r+N, ... on its own grid replica, no exchange "
+                                    "(opt-in; the default is BASELINE's sort-first tile split of one frame)",
+                       "frame_latency_ms": round(ms_per_step, 4), "ms_per_frame_throughput": round(ms_per_step / world, 4),
+                       "l2": "flushed between timed frames (256 MiB write)", "timing": "CUDA events on the launching stream per frame, max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": round(world * rays / (e2e_s / args.steps) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(e2e_s / args.steps * 1e3, 4),
+                    "h2d_bytes_per_step": 360 * world, "d2h_bytes_per_step": W * H * 4 * world,
+                    "api": "every rank: vxrt_submit_frame_host x K + vxrt_wait_frames (host frame params in, host RGBA8 frame out, own PCIe link); wall clock / K, max over ranks"},
+            "gpu_launches": int(args.steps * st["kernel_launches"] * world),
+            "roofline": {"bound": "hbm", "kernel": "shade_kernel", "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s",
+                         "frac": round(achieved / hbm, 5), "traffic": None, "peak_source": peak_src,
+                         "kernels": {"primary_kernel": {"ms": round(prim_ms, 4)}, "shade_kernel": {"ms": round(shade_ms, 4), "alg_bytes": int(bytes_shade)}}},
+        }
+    dist.barrier()
+    dist.destroy_process_group()
+    del flush
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    ren.close()
+    if rank == 0:
+        print(json.dumps(result))
+
+
+# =====================================================================================================
 def reference_frame_runner(workload, stride, level=None):
     """Returns (run_once() -> seconds, rays_in_sample, kind, cores, sample_description).  Uses the reference's own
     shader compiled for the CPU (oracle/_ref/ref_shader_cli, all host cores via fork) when that build travelled
@@ -676,5 +805,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.partition == "frames" and a.gpus > 1:
+        run_frame_sharded(a)
     else:
         run_b200(a)
