@@ -76,6 +76,19 @@ def test_cast_ray_known_answers(vx, oracle, golden, ren):
     assert h64(oracle, out7) == g["out7_fnv"]
 
 
+def test_tie_lock_ray(vx, oracle, default_level, ren):
+    """fshader.glsl:87-104 with intersect.x == intersect.y < intersect.z: the else branch steps z for the rest of the segment
+    (tests/test_oracle_quirks.py); both loop forms of ray.cuh (even index: compiler-scheduled, odd: PTX empty-cell runs)"""
+    import test_oracle_quirks as q
+    starts = np.array([q.TIE_START, q.TIE_START], np.float32)
+    dirs = np.array([q.TIE_DIR, q.TIE_DIR], np.float32)
+    ret, out7 = ren.castRays(starts, dirs, np.array([q.TIE_DIST, q.TIE_DIST], np.int32))
+    r, hp, hn, st = oracle.cast_ray(default_level, gc.DIMS, q.TIE_START, q.TIE_DIR, q.TIE_DIST)
+    assert r == 7391987 and [int(v) for v in ret] == [r, r]
+    for k in range(2):
+        assert np.array_equal(out7[k][:3].view(np.uint32), hp.view(np.uint32)) and list(out7[k][3:6]) == list(hn) and out7[k][6] == st
+
+
 def test_fast_division_matches_ieee(vx, ren):
     """ray.cuh div_by (hoisted reciprocal + 3 FFMA) == __fdiv_rn on 2^31 random operand pairs of its domain"""
     assert ren.selftestDivision(1 << 31, seed=12345) == 0
