@@ -354,6 +354,24 @@ static int boxes_are_clear(float sx, float sy, float sz, float rx, float ry, flo
 static const int BOX_K[VXO_BOX_VARIANTS] = {1, 2, 4, 8, 16, 8, 8, 16};
 static const int BOX_Q[VXO_BOX_VARIANTS] = {1, 1, 1, 1, 1, 2, 4, 4};
 
+/* Check of the guards of ray.cuh's FAST_RUNS experiment (same integer / float operations).  Before a step of a shadow / light
+ * ray that is not inside a run: if the wrapped index terms of the cell are at least FAST_RUN_MARGIN cells away from every
+ * bound, a run of steps without range test begins; it ends when distTravelled reaches stop = min(limit, distTravelled0 +
+ * (FAST_RUN_MARGIN - 1) - 0.5) or at the first voxel that is not empty.  Every step of a run is checked here to be in the
+ * grid and to pass the reference's budget test, and no run to take more than FAST_RUN_MARGIN - 1 steps. */
+#define FAST_RUN_MARGIN 8
+typedef struct { int left, taken; float stop; } fast_run;
+static void fast_arm(fast_run* fr, vxo_dims g, int cx, int cy, int cz, float limit, float dist) {
+    const uint32_t W = (uint32_t)g.w, WH = W * (uint32_t)g.h, N = WH * (uint32_t)g.d, M = FAST_RUN_MARGIN;
+    const uint32_t px = (uint32_t)cx, py = (uint32_t)cy * W, pz = (uint32_t)cz * WH;
+    const uint32_t tx = g.w > 2 * FAST_RUN_MARGIN ? W - 2 * M : 0, ty = g.h > 2 * FAST_RUN_MARGIN ? WH - 2 * M * W : 0,
+                   tz = g.d > 2 * FAST_RUN_MARGIN ? N - 2 * M * WH : 0;
+    fr->left = (px - M < tx) && (py - M * W < ty) && (pz - M * WH < tz);
+    fr->taken = 0;
+    const float s2 = dist + ((float)(FAST_RUN_MARGIN - 1) - 0.5f);
+    fr->stop = limit < s2 ? limit : s2;
+}
+
 static void prof_ray(int outcome, uint64_t it, uint64_t jumps, uint64_t cull_it) {
     vxo_profile* p = tl_prof;
     if (!p) return;
@@ -383,6 +401,9 @@ static int32_t cast_ray(const int32_t* vox, vxo_dims g, shader_state* st,
     int p_outcome = 2;                                              /* 0 hit, 1 left the grid, 2 budget exhausted */
     if (tl_prof && ((stepy > 0 && cy > tl_ymax) || (stepy < 0 && cy < tl_ymin))) p_cull = 0;
     int p_clear[VXO_BOX_VARIANTS] = {0};
+    fast_run fr = {0, 0, 0.0f};
+    const float p_lim = (float)dist < (float)RENDER_DIST ? (float)dist : (float)RENDER_DIST;
+
     if (tl_prof && sat && tl_kind != 0 && !tl_dark) {
         const float lim = (float)dist < (float)RENDER_DIST ? (float)dist : (float)RENDER_DIST;
         for (int v = 0; v < VXO_BOX_VARIANTS; v++) p_clear[v] = boxes_are_clear(sx, sy, sz, rx, ry, rz, lim, BOX_K[v], BOX_Q[v]);
@@ -391,6 +412,10 @@ static int32_t cast_ray(const int32_t* vox, vxo_dims g, shader_state* st,
         st->stepCount = st->stepCount + 1.0f;                       /* :84 */
         st->fetches++;
         p_it++;
+        if (tl_prof && tl_kind != 0 && fr.left == 0) {              /* analysis only: would an unchecked run begin here? */
+            fast_arm(&fr, g, cx, cy, cz, p_lim, distTravelled);
+            if (fr.left) tl_prof->fast_runs++;
+        }
         distTravelled = distTravelled + 1.0f;                       /* :85 */
         if (ix < iy && ix < iz) {                                   /* :87-92 */
             currDist = ix; cx = (int32_t)((uint32_t)cx + (uint32_t)stepx); ix = ix + dx;
@@ -403,6 +428,13 @@ static int32_t cast_ray(const int32_t* vox, vxo_dims g, shader_state* st,
             st->hitNormal[0] = 0.0f; st->hitNormal[1] = 0.0f; st->hitNormal[2] = (float)(-stepz);
         }
         tempIndex = vxo_shader_index(g, cx, cy, cz);                /* :105 */
+        if (tl_prof && fr.left > 0) {                               /* analysis only: a step of an unchecked run */
+            fr.taken++; tl_prof->fast_steps++;
+            if (tempIndex < 0 || fr.taken > FAST_RUN_MARGIN - 1) tl_prof->fast_guard_violations++;   /* left the grid / ran too long */
+            if (tempIndex >= 0 && vox[tempIndex] != -1) fr.left = 0;   /* event: the run ends here */
+            else if (!(distTravelled < fr.stop)) fr.left = 0;       /* the run is over: the checked block takes the next step ... */
+            else if (!(distTravelled < p_lim)) tl_prof->fast_guard_violations++;   /* ... and a step the reference would not take never starts */
+        }
         if (tempIndex >= 0 && vox[tempIndex] >= 0) {                /* :108-112 */
             st->hitPos[0] = rx * currDist + sx;
             st->hitPos[1] = ry * currDist + sy;
@@ -634,6 +666,7 @@ void vxo_profile_frame(const int32_t* vox, vxo_dims g, const vxo_frame* f, int w
                     a->iterations_dark += b->iterations_dark; a->iterations_dark_after_cull += b->iterations_dark_after_cull;
                 }
                 if (loc.longest[k] > out->longest[k]) out->longest[k] = loc.longest[k];
+                if (k == 0) { out->fast_runs += loc.fast_runs; out->fast_steps += loc.fast_steps; out->fast_guard_violations += loc.fast_guard_violations; }
                 for (int v = 0; v < VXO_BOX_VARIANTS; v++) {
                     out->box[k][v].rays += loc.box[k][v].rays; out->box[k][v].iterations += loc.box[k][v].iterations;
                     out->box[k][v].violations += loc.box[k][v].violations;

@@ -129,6 +129,7 @@ typedef struct {
     vxo_profile_cell cell[3][3];
     vxo_profile_box box[3][VXO_BOX_VARIANTS];
     uint64_t longest[3];            /* most iterations of a single ray, per kind */
+    uint64_t fast_runs, fast_steps, fast_guard_violations;   /* ray.cuh FAST_RUNS: unchecked runs, their steps, failed guards (must be 0) */
     int32_t ymin, ymax;             /* rows that hold a solid voxel */
 } vxo_profile;
 void vxo_profile_frame(const int32_t* vox, vxo_dims g, const vxo_frame* f, int width, int height, vxo_profile* out);

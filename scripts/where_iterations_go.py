@@ -33,7 +33,7 @@ BOX_KQ = ((1, 1), (2, 1), (4, 1), (8, 1), (16, 1), (8, 2), (8, 4), (16, 4))
 
 
 class Profile(C.Structure):
-    _fields_ = [("cell", (Cell * 3) * 3), ("box", (Box * 8) * 3), ("longest", C.c_uint64 * 3), ("ymin", C.c_int32), ("ymax", C.c_int32)]
+    _fields_ = [("cell", (Cell * 3) * 3), ("box", (Box * 8) * 3), ("longest", C.c_uint64 * 3), ("fast_runs", C.c_uint64), ("fast_steps", C.c_uint64), ("fast_guard_violations", C.c_uint64), ("ymin", C.c_int32), ("ymax", C.c_int32)]
 
 
 KINDS = ("primary", "global_light", "local_light")
@@ -44,7 +44,8 @@ def profile(o, level, dims, frame, w, h):
     p = Profile()
     o.L.vxo_profile_frame.restype = None
     o.L.vxo_profile_frame(level.ctypes.data_as(C.POINTER(C.c_int32)), ol.Dims(*dims), C.byref(frame), C.c_int(w), C.c_int(h), C.byref(p))
-    out = {"ymin": p.ymin, "ymax": p.ymax, "longest": {k: int(p.longest[i]) for i, k in enumerate(KINDS)}, "cells": {},
+    out = {"fast_runs": {"runs": int(p.fast_runs), "steps": int(p.fast_steps), "guard_violations": int(p.fast_guard_violations)},
+           "ymin": p.ymin, "ymax": p.ymax, "longest": {k: int(p.longest[i]) for i, k in enumerate(KINDS)}, "cells": {},
            "clear_box": {"%s/k%d_q%d" % (k, kq[0], kq[1]): {"rays": int(p.box[i][v].rays), "iterations_saved": int(p.box[i][v].iterations),
                                              "violations": int(p.box[i][v].violations)}
                          for i, k in enumerate(KINDS) if i for v, kq in enumerate(BOX_KQ)}}
@@ -98,6 +99,9 @@ def main():
                     k, c["rays"], c["iterations"], c["iterations"] / c["rays"], 100.0 * c["jumps"] / max(1, c["iterations"]),
                     c["iterations_after_cull"], c["iterations_dark"]))
         print("  " + json.dumps(s))
+        shadow_it = sum(c["iterations"] for k, c in pr["cells"].items() if not k.startswith("primary/"))
+        print("  FAST_RUNS experiment (ray.cuh): %d unchecked runs cover %d of the %d iterations of shadow / light rays (%.1f%%), guard violations %d" % (
+            pr["fast_runs"]["runs"], pr["fast_runs"]["steps"], shadow_it, 100.0 * pr["fast_runs"]["steps"] / max(1, shadow_it), pr["fast_runs"]["guard_violations"]))
         for k, b in pr["clear_box"].items():
             print("  clear box %-24s rays %10d  iterations saved %11d (%.1f%% of those still executed)  violations %d" % (
                 k, b["rays"], b["iterations_saved"], 100.0 * b["iterations_saved"] / s["still_executed"], b["violations"]))

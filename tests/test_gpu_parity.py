@@ -692,3 +692,45 @@ def test_local_light_slots(vx):
         assert list(f.lights[15]) == [16.0, 2.0, 3.0, 0.5]
         r.reshape(64, 16)
         assert r.getFrame().aspect == 4.0                                          # reshape, render.cpp:410
+
+
+# ---- experiments (off by default in the library; their tests are gated until they have run on a B200 once) ------------
+@pytest.mark.skipif(os.environ.get("VXRT_TEST_EXPERIMENTS") != "1",
+                    reason="ray.cuh FAST_RUNS experiment: written after round 1's GPU budget was spent, VXRT_TEST_EXPERIMENTS=1 enables it")
+def test_fast_runs_experiment_is_bit_exact(vx, oracle, golden, default_level, monkeypatch):
+    """VXRT_FAST_RUNS=1: shadow / light rays take runs of empty cells without the range tests (ray.cuh).  Same frames, same
+    debug planes, same counters as the oracle; castRay known answers incl. the tie-lock ray and rays next to the faces."""
+    import test_oracle_quirks as q
+    monkeypatch.setenv("VXRT_FAST_RUNS", "1")
+    with vx.Renderer(grid=gc.DIMS, width=160, height=90, debug=True) as r:
+        r.updateGeometry(default_level)
+        for name, W, H in (("C2", 1920, 1080), ("C3ii_pitched", 1280, 720), ("low_sun", 640, 360), ("sparse_lights", 416, 240)):
+            check_frame(vx, oracle, r, default_level, gc.DIMS, gc.frame_cases(W, H)[name], W, H)
+        g = golden["ref_shader"]["kat"]
+        starts, dirs, dists = gc.kat_rays(g["n"], g["seed"])
+        ret, out7 = r.castRays(starts, dirs, dists)
+        assert h64(oracle, ret) == g["ret_fnv"] and h64(oracle, out7) == g["out7_fnv"]
+        ret, out7 = r.castRays(np.array([q.TIE_START] * 2, np.float32), np.array([q.TIE_DIR] * 2, np.float32), np.array([q.TIE_DIST] * 2, np.int32))
+        assert [int(v) for v in ret] == [7391987, 7391987] and out7[1][6] == 61.0
+    # a small grid (every cell within the margin of a face: no run may start) and production frames (counters off)
+    dims = (40, 24, 40)
+    rs = np.random.RandomState(5)
+    level = np.full(dims[0] * dims[1] * dims[2], -1, np.int32)
+    gv = level.reshape(dims[2], dims[1], dims[0])
+    gv[:, :6, :] = 0x406040
+    for _ in range(12):
+        x, y, z = rs.randint(2, 38), rs.randint(6, 16), rs.randint(2, 38)
+        gv[z - 1:z + 2, 6:y, x - 1:x + 2] = int(rs.randint(0, 1 << 24))
+    oracle.compute_depth_field(level, dims)
+    import oracle_lib as ol
+    fr = ol.make_frame((20.0, 14.0, 3.0), aspect=np.float32(16) / np.float32(9), light_pos=(20.0, 120.0, 20.0),
+                       lights=[(8.0 + 6 * i, 9.0, 10.0 + 5 * i, 0.5) for i in range(5)])
+    with vx.Renderer(grid=dims, width=256, height=144, debug=True) as r:
+        r.updateGeometry(level)
+        check_frame(vx, oracle, r, level, dims, fr, 256, 144)
+    with vx.Renderer(grid=gc.DIMS, width=640, height=360) as r:        # production variant: no counters, culling on
+        r.updateGeometry(default_level)
+        r.setStats(False)
+        fr = gc.frame_cases(640, 360)["C2"]
+        got = r.renderFrameHost(to_vx_frame(vx, fr))
+        assert np.array_equal(got, oracle.render(default_level, gc.DIMS, fr, 640, 360)["rgba8"])

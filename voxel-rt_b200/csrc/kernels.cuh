@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __rest
     }
 }
 
-template <bool COUNT, class Grid>
+// FAST: the shadow / light rays use ray.cuh's FAST_RUNS experiment (unchecked runs of empty cells; off by default)
+template <bool COUNT, class Grid, bool FAST = false>
 __global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_constant__ FrameParams f,
                                                     TileMap m, Outputs o) {
     __shared__ float4 s_light[16];          // compacted active lights (slot order preserved)
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_cons
         if (COUNT && !g_lit) ndark++;
         if (g_lit || !skip_dark) {   // :154 global-light shadow ray
             normalize3(lx, ly, lz);
-            const RayHit s = cast_ray<COUNT, true, true>(g, __fadd_rn(hx, __fmul_rn(lx, 0.001f)), __fadd_rn(hy, __fmul_rn(ly, 0.001f)),
+            const RayHit s = cast_ray<COUNT, true, true, Grid, FAST>(g, __fadd_rn(hx, __fmul_rn(lx, 0.001f)), __fadd_rn(hy, __fmul_rn(ly, 0.001f)),
                                       __fadd_rn(hz, __fmul_rn(lz, 0.001f)), lx, ly, lz, VXRT_RENDER_DIST);
             fetches += (unsigned)s.steps;
             if (s.idx == -1) multiplier = __fadd_rn(multiplier, __fmul_rn(VXRT_DIFFUSE, max0(dot3(nx, ny, nz, lx, ly, lz))));   // :155
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_cons
                 normalize3_with_length(tx, ty, tz, lld);                                    // :173 (same dot, same sqrt as :168)
                 cast |= 2u << slot; nlocal++;
                 if (COUNT && !lit) ndark++;
-                const RayHit s = cast_ray<COUNT, true, false>(g, __fadd_rn(hx, __fmul_rn(tx, 0.001f)), __fadd_rn(hy, __fmul_rn(ty, 0.001f)),
+                const RayHit s = cast_ray<COUNT, true, false, Grid, FAST>(g, __fadd_rn(hx, __fmul_rn(tx, 0.001f)), __fadd_rn(hy, __fmul_rn(ty, 0.001f)),
                                           __fadd_rn(hz, __fmul_rn(tz, 0.001f)), tx, ty, tz, f2i(__fadd_rn(lld, 1.0f)));   // :175
                 fetches += (unsigned)s.steps;
                 if (s.idx == -1) {                                                          // :177
@@ -394,11 +395,12 @@ __global__ void scatter_rows_kernel(int32_t* __restrict__ vox, const int32_t* __
 }
 
 // known-answer hook: n independent castRay calls
+template <bool FAST = false>
 __global__ void cast_rays_kernel(GridView g, int n, const float* __restrict__ starts, const float* __restrict__ dirs,
                                  const int32_t* __restrict__ dists, int32_t* __restrict__ ret, float* __restrict__ out7) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const RayHit r = (i & 1) ? cast_ray<true, true, false>(g, starts[3 * i], starts[3 * i + 1], starts[3 * i + 2], dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], dists[i])
+    const RayHit r = (i & 1) ? cast_ray<true, true, false, GridView, FAST>(g, starts[3 * i], starts[3 * i + 1], starts[3 * i + 2], dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], dists[i])
                              : cast_ray<true, false, false>(g, starts[3 * i], starts[3 * i + 1], starts[3 * i + 2], dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], dists[i]);
     ret[i] = r.idx;
     float nx, ny, nz;

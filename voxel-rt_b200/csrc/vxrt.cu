@@ -80,6 +80,7 @@ struct vxrt_ctx {
     bool use_tile_order = true;
     bool use_culling = true;
     int l2_prefetch = 2;                // vxrt_set_l2_prefetch: 0 off, 1 on, 2 auto (on when this context renders <= 12,000 tiles)
+    bool fast_runs = false;             // EXPERIMENT (VXRT_FAST_RUNS=1): shadow / light rays use ray.cuh's unchecked runs of empty cells
     int shade_threads = 128;            // threads per shade block (VXRT_SHADE_THREADS: 64 / 128 / 256; 128 measured best)
     int32_t* d_dbg_hit = nullptr;
     uint16_t* d_dbg_steps = nullptr;
@@ -318,6 +319,7 @@ extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     for (int i = 0; i < 4; i++) c->frame.rotate[5 * i] = 1.0f;
     vxrt_init_local_lights(c);
     if (const char* e = getenv("VXRT_L2_PREFETCH")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->l2_prefetch = v; }
+    if (const char* e = getenv("VXRT_FAST_RUNS")) c->fast_runs = atoi(e) == 1;
     if (const char* e = getenv("VXRT_SHADE_THREADS")) {
         const int v = atoi(e);
         if (v == 64 || v == 128 || v == 256) c->shade_threads = v;
@@ -773,10 +775,16 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         if (c->frame.view_depth_field != 1) {
             const dim3 sblock(c->shade_threads), sgrid((unsigned)(((size_t)ntile * TILE_PIX + c->shade_threads - 1) / c->shade_threads));
             if (ref_dims) {
-                if (count) shade_kernel<true, GridViewRef><<<sgrid, sblock, 0, c->stream>>>(gr, fp, m, o);
+                if (c->fast_runs) {
+                    if (count) shade_kernel<true, GridViewRef, true><<<sgrid, sblock, 0, c->stream>>>(gr, fp, m, o);
+                    else shade_kernel<false, GridViewRef, true><<<sgrid, sblock, 0, c->stream>>>(gr, fp, m, o);
+                } else if (count) shade_kernel<true, GridViewRef><<<sgrid, sblock, 0, c->stream>>>(gr, fp, m, o);
                 else shade_kernel<false, GridViewRef><<<sgrid, sblock, 0, c->stream>>>(gr, fp, m, o);
             } else {
-                if (count) shade_kernel<true, GridView><<<sgrid, sblock, 0, c->stream>>>(g, fp, m, o);
+                if (c->fast_runs) {
+                    if (count) shade_kernel<true, GridView, true><<<sgrid, sblock, 0, c->stream>>>(g, fp, m, o);
+                    else shade_kernel<false, GridView, true><<<sgrid, sblock, 0, c->stream>>>(g, fp, m, o);
+                } else if (count) shade_kernel<true, GridView><<<sgrid, sblock, 0, c->stream>>>(g, fp, m, o);
                 else shade_kernel<false, GridView><<<sgrid, sblock, 0, c->stream>>>(g, fp, m, o);
             }
             CUDA_TRY(cudaGetLastError());
@@ -1000,7 +1008,8 @@ extern "C" int vxrt_cast_rays(vxrt_ctx* c, int32_t n, const float* starts, const
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dirs, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, dists, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) {
-        cast_rays_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(grid_view(c), n, d_s, d_d, d_n, d_r, d_o);
+        if (c->fast_runs) cast_rays_kernel<true><<<(n + 127) / 128, 128, 0, c->stream>>>(grid_view(c), n, d_s, d_d, d_n, d_r, d_o);
+        else cast_rays_kernel<false><<<(n + 127) / 128, 128, 0, c->stream>>>(grid_view(c), n, d_s, d_d, d_n, d_r, d_o);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(ret, d_r, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream);
