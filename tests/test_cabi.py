@@ -78,3 +78,14 @@ def test_frame_struct_layout(vx):
     import oracle_lib as ol
     assert C.sizeof(vx.Frame) == C.sizeof(ol.Frame) == 360          # 90 scalars, SURVEY.md a2
     assert [f[0] for f in vx.Frame._fields_] == [f[0] for f in ol.Frame._fields_]
+
+
+def test_documents_name_only_entry_points_that_exist():
+    """INTEGRATION.md / DESIGN.md / README.md show reference-side bindings: every vxrt_* name in them is declared in include/vxrt.h
+    (or is one of the repo's file / binary names)"""
+    text = open(os.path.join(ROOT, "include", "vxrt.h")).read()
+    declared = set(re.findall(r"\b(vxrt_[a-z0-9_]+)\b", text))
+    files = {"vxrt_controls", "vxrt_headless", "vxrt_render", "vxrt_glshim", "vxrt_host_frame_", "vxrt_p2p_"}
+    for doc in ("INTEGRATION.md", "DESIGN.md", "README.md", os.path.join("profiles", "README.md"), os.path.join("scripts", "README.md")):
+        names = set(re.findall(r"\b(vxrt_[a-z0-9_]+)\b", open(os.path.join(ROOT, doc)).read()))
+        assert names <= declared | files, (doc, sorted(names - declared - files))
