@@ -3,7 +3,9 @@ NO occupancy structure ever save?  Every ray of a frame is classified by kind (p
 by how it ended (hit / left the grid / budget exhausted).  A ray that hits must run every iteration (the first-hit voxel
 and hitPos depend on the whole float state), so only the iterations of rays that end as misses are avoidable at all;
 of those the table shows what the CUDA path already removes (occupancy-summary culling, unlit rays) and what is left for
-any finer brick hierarchy.  Usage: python scripts/where_iterations_go.py [--size 3840 2160] [--case C3ii C3ii_pitched]
+any finer brick hierarchy.  Two experiments ride along: the "clear tube" test (summed-area table of solid voxels: is the
+tube between a surface point and its light empty?) with the number of rays that HIT although their tube is clear (tie locks),
+and a replay of the guards of ray.cuh's FAST_RUNS experiment on every shadow / light ray.  Usage: python scripts/where_iterations_go.py [--size 3840 2160] [--case C3ii C3ii_pitched]
 Writes profiles/r1_where_iterations_go.json with --write."""
 import argparse
 import ctypes as C
