@@ -9,3 +9,8 @@ bash scripts/gpu_glshim.sh
 bash scripts/gpu_fast_runs.sh
 # per-kernel times of the experiment on both poses, twice (exp_time.py)
 bash scripts/gpu_exp_variant.sh VXRT_FAST_RUNS=0 VXRT_FAST_RUNS=1
+# experiment variants that change the render kernels' SASS live in libraries of their own (voxel_rt_b200.build.VARIANTS):
+# the whole parity suite on the variant, then its kernel times next to the default library's
+python voxel-rt_b200/build.py late_domain_check | tail -1
+VXRT_LIB=$PWD/voxel-rt_b200/libvxrt_exp_late_domain_check.so python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+bash scripts/gpu_exp_variant.sh VXRT_FAST_RUNS=0 VXRT_LIB=voxel-rt_b200/libvxrt_exp_late_domain_check.so

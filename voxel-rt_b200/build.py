@@ -96,8 +96,33 @@ def build(force=False, verbose=False):
     return LIB
 
 
+VARIANTS = {
+    # name -> extra nvcc flags; experiments that change the SASS of the render kernels live behind macros so that the
+    # default library stays exactly what was validated (scripts/gpu_exp_variant.sh times them, VXRT_LIB=... pytest -m gpu
+    # runs the whole parity suite on one)
+    "late_domain_check": ["-DVXRT_EXP_LATE_DOMAIN_CHECK"],
+}
+
+
+def build_variant(name, verbose=False):
+    """libvxrt_exp_<name>.so: the library compiled with one experiment's macro (see VARIANTS)"""
+    out = os.path.join(HERE, "libvxrt_exp_%s.so" % name)
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + VARIANTS[name] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building " + out)
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_host(force="--force" in sys.argv))
     print(build_hostlogic(force="--force" in sys.argv))
     print(build_glshim(force="--force" in sys.argv))
+    for v in sys.argv[1:]:
+        if v in VARIANTS:
+            print(build_variant(v))
