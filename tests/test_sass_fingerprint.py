@@ -1,0 +1,33 @@
+"""CPU: the kernels in the built libvxrt.so are, instruction for instruction, the ones whose B200 measurements are committed
+under profiles/ (tests/golden/sass_fingerprints.json, made by tests/golden/make_sass_fingerprints.py).  Experiments live
+behind template parameters / macros that leave the production kernels' SASS untouched; changing a production kernel means
+regenerating the fingerprints on purpose -- and measuring again."""
+import json
+import os
+import re
+import shutil
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+
+def is_experiment(name):
+    return bool(re.search(r"shade_kernel<\w+, vxrt::GridView(Ref)?, true>|cast_rays_kernel<true>", name))
+
+
+def test_production_kernels_are_the_measured_ones(vx):
+    if not (shutil.which("cuobjdump") and shutil.which("c++filt") and shutil.which("nvcc")):
+        pytest.skip("cuobjdump / c++filt / nvcc unavailable")
+    import make_sass_fingerprints as msf
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "sass_fingerprints.json")))
+    if msf.nvcc_version() != want["nvcc"]:
+        pytest.skip("fingerprints were made with nvcc %s" % want["nvcc"])
+    got = msf.fingerprints(vx.build.LIB)
+    assert set(got) == set(want["kernels"])
+    changed = sorted(k for k in got if got[k] != want["kernels"][k])
+    assert not changed, changed
+    production = [k for k in got if not is_experiment(k)]
+    assert len(production) == 27 and len(got) - len(production) == 5          # 4 shade + 1 known-answer variants of FAST_RUNS
