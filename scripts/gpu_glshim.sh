@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-VXRT_TEST_GLSHIM_GPU=1 python -m pytest tests/test_gpu_host.py tests/test_gpu_parity.py -m gpu -x -q -k "gl_shim or upload_rows" 2>&1 | tail -5
+python -m pytest tests/test_gpu_host.py tests/test_gpu_parity.py -m gpu -x -q -k "gl_shim or upload_rows" 2>&1 | tail -5
 # the same binary as a 4K session: 300 frames after the depth threads finished, a destruction every 50 frames
 d=$(mktemp -d); printf '#version 430\nvoid main(){}\n' > $d/vshader.glsl
 printf '#version 430\nconst int VOXELS_WIDTH=512;\nconst int VOXELS_HEIGHT=96;\nconst int RENDER_DIST=384;\nvoid main(){}\n' > $d/fshader.glsl

@@ -111,9 +111,9 @@ GAME = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
 
 
 @pytest.mark.skipif(not os.path.exists(GAME), reason="oracle/_ref/voxel_rt_on_vxrt not built (make -C oracle ref)")
-@pytest.mark.skipif(os.environ.get("VXRT_TEST_GLSHIM_GPU") != "1",
-                    reason="written after round 1's GPU budget was spent: not run on a B200 yet; VXRT_TEST_GLSHIM_GPU=1 enables it "
-                           "(the same session against an oracle-backed mock libvxrt runs on the CPU: tests/test_glshim.py)")
+@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: its first run on a B200 is the round-end run itself. The game "
+                                         "is a separate process, so a failure cannot disturb the parity tests; the same session against an "
+                                         "oracle-backed mock libvxrt passes on the CPU (tests/test_glshim.py)")
 def test_reference_game_on_the_b200_through_the_gl_shim(vx, oracle, default_level, tmp_path):
     """oracle/_ref/voxel_rt_on_vxrt = the reference's six objects, unmodified, linked against libvxrt_glshim.so + libvxrt.so:
     its own main loop (main.cpp:47-75) with scripted input -- look down, place a light, right-click destruction (900
@@ -125,7 +125,7 @@ def test_reference_game_on_the_b200_through_the_gl_shim(vx, oracle, default_leve
     r = tg.run_game(tg.shader_dir(tmp_path), {
         "VXRT_GLSHIM_READY_UPLOADS": "2", "VXRT_GLSHIM_FRAMES": "24", "VXRT_GLSHIM_FPS": "60", "VXRT_GLSHIM_EVENTS": script,
         "VXRT_GLSHIM_DUMP": str(tmp_path / "f%02d.ppm"), "VXRT_GLSHIM_DUMP_FRAMES": "11,12,14,20", "VXRT_GLSHIM_LOG": "1",
-        "VXRT_GLSHIM_SAVE_GRID": str(tmp_path / "final.vxg")})
+        "VXRT_GLSHIM_SAVE_GRID": str(tmp_path / "final.vxg")}, timeout=240)
     assert r.returncode == 0, r.stderr
     assert "24 frames at 640x360" in r.stderr and "900 glBufferSubData calls in 1 batches" in r.stderr
 
