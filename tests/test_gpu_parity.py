@@ -695,6 +695,18 @@ def test_local_light_slots(vx):
 
 
 # ---- experiments (off by default in the library; their tests are gated until they have run on a B200 once) ------------
+@pytest.mark.xfail(strict=False, reason="ray.cuh FAST_RUNS experiment (off by default): written after round 1's GPU budget was spent, its first run on a "
+                                         "B200 is the round-end run.  It runs in a process of its own (new device code: a fault must not touch the "
+                                         "CUDA context of the parity tests); xpassed = the experiment is bit-exact on the real GPU")
+def test_fast_runs_experiment_in_a_subprocess():
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "fast_runs_check.py")], env=dict(os.environ, VXRT_FAST_RUNS="1"),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "FAST_RUNS ok" in r.stdout, (r.stdout + r.stderr)[-2000:]
+
+
 @pytest.mark.skipif(os.environ.get("VXRT_TEST_EXPERIMENTS") != "1",
                     reason="ray.cuh FAST_RUNS experiment: written after round 1's GPU budget was spent, VXRT_TEST_EXPERIMENTS=1 enables it")
 def test_fast_runs_experiment_is_bit_exact(vx, oracle, golden, default_level, monkeypatch):
