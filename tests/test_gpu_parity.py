@@ -699,12 +699,33 @@ def test_local_light_slots(vx):
                                          "B200 is the round-end run.  It runs in a process of its own (new device code: a fault must not touch the "
                                          "CUDA context of the parity tests); xpassed = the experiment is bit-exact on the real GPU")
 def test_fast_runs_experiment_in_a_subprocess():
+    out = run_variant_check("FAST_RUNS", VXRT_FAST_RUNS="1")
+    assert "FAST_RUNS ok" in out
+
+
+def run_variant_check(label, **env):
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, os.path.join(here, "fast_runs_check.py")], env=dict(os.environ, VXRT_FAST_RUNS="1"),
+    r = subprocess.run([sys.executable, os.path.join(here, "variant_check.py"), label], env=dict(os.environ, **env),
                        capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and "FAST_RUNS ok" in r.stdout, (r.stdout + r.stderr)[-2000:]
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    return r.stdout
+
+
+@pytest.mark.xfail(strict=False, reason="variant library libvxrt_exp_late_domain_check.so (ray.cuh VXRT_EXP_LATE_DOMAIN_CHECK: divide before the domain test, "
+                                         "so that the shade kernel stops computing the re-base dividends twice): written after round 1's GPU budget was "
+                                         "spent; built here with nvcc and checked in a process of its own; xpassed = bit-exact on the real GPU")
+def test_late_domain_check_variant_in_a_subprocess(vx):
+    import shutil
+    if not shutil.which(os.environ.get("NVCC", "nvcc")):
+        pytest.skip("nvcc unavailable")
+    lib = vx.build.build_variant("late_domain_check")
+    try:
+        out = run_variant_check("late_domain_check", VXRT_LIB=lib)
+        assert "late_domain_check ok" in out and os.path.basename(lib) in out
+    finally:
+        os.remove(lib)
 
 
 @pytest.mark.skipif(os.environ.get("VXRT_TEST_EXPERIMENTS") != "1",

@@ -1,6 +1,7 @@
-"""Run in a process of its own (tests/test_gpu_parity.py::test_fast_runs_experiment_in_a_subprocess): frames and known answers of
-the FAST_RUNS experiment of ray.cuh (VXRT_FAST_RUNS=1, set by the caller) against the oracle.  A process of its own because
-the experiment is new device code: if it faulted, the CUDA context of the parity tests would be unusable."""
+"""Run in a process of its own (tests/test_gpu_parity.py::test_*_in_a_subprocess): frames and known answers of a kernel experiment
+against the oracle -- the FAST_RUNS experiment of ray.cuh (VXRT_FAST_RUNS=1) or a variant library (VXRT_LIB=...), chosen by
+the caller through the environment.  A process of its own because an experiment is new device code: if it faulted, the CUDA
+context of the parity tests would be unusable.  Usage: python tests/variant_check.py <label>"""
 import os
 import sys
 
@@ -17,7 +18,11 @@ import voxel_rt_b200 as vx  # noqa: E402
 
 
 def main():
-    assert os.environ.get("VXRT_FAST_RUNS") == "1"
+    label = sys.argv[1] if len(sys.argv) > 1 else "default"
+    if label == "FAST_RUNS":
+        assert os.environ.get("VXRT_FAST_RUNS") == "1"
+    elif label != "default":
+        assert os.path.basename(os.environ.get("VXRT_LIB", "")) == "libvxrt_exp_%s.so" % label, os.environ.get("VXRT_LIB")
     ol.build_oracle()
     o = ol.Oracle()
     level = conftest.load_default_level(o)
@@ -45,7 +50,7 @@ def main():
         fr = gc.frame_cases(640, 360)["C2"]
         got = r.renderFrameHost(vx.Frame.from_buffer_copy(bytes(fr)))
         assert np.array_equal(got, o.render(level, gc.DIMS, fr, 640, 360)["rgba8"]), "production frame"
-    print("FAST_RUNS ok: %d counted frames, the tie-lock ray, 1 production frame" % checked)
+    print("%s ok: %d counted frames, the tie-lock ray, 1 production frame (%s)" % (label, checked, vx.build.lib_path()))
 
 
 if __name__ == "__main__":
