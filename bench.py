@@ -535,8 +535,10 @@ def run_b200(args):
         if scene == "C5":
             result["config"]["edits"] = "one vxrt_edit_remove_sphere(r=7) per frame, centres from mt19937(12345); rays/fetches are those of the last frame"
         if not args.no_extra and world == 1 and scene not in ("C4", "C5"):
+            production_fnv = "%016x" % vx.scenes.fnv1a64(host_out)          # the frame the e2e loop delivered
             result["other_workloads"] = extra_workloads(vx, ren, flush_l2, stream, torch)
             result["cpu_baseline"] = cpu_baseline(args.workload, level=level_arr)
+            result["experiments"] = experiments(args.workload, production_fnv)
     # teardown order matters: torch tensors that were used on the renderer's stream must be released (their
     # allocator records events on that stream) BEFORE the renderer destroys it
     if world > 1:
@@ -577,6 +579,43 @@ def extra_workloads(vx, ren, flush_l2, stream, torch, steps=10):
         m = statistics.mean(ms)
         out[name] = {"ms_per_frame": round(m, 4), "Mrays_per_s": round(rays / (m * 1e-3) / 1e6, 2), "rays_per_frame": rays,
                      "voxel_fetches_per_frame": st["fetches"]}
+    return out
+
+
+def experiments(workload, production_fnv):
+    """Kernel experiments that are NOT in the numbers above (off by default / separate libraries), each timed and
+    checked in a process of its own by scripts/exp_probe.py after the measurements of this line are complete: the production
+    library through the same probe (the figure to compare with), ray.cuh FAST_RUNS, and the late-domain-check variant library.
+    "bit_exact": the probe's frame has the fingerprint of the production frame.  Never raises: a failing experiment is a note."""
+    import shutil
+    import voxel_rt_b200 as vx
+    probe = os.path.join(ROOT, "scripts", "exp_probe.py")
+    out = {"note": "not part of value / e2e; same workload, scripts/exp_probe.py, one process each", "production_frame_fnv": production_fnv}
+
+    def run(label, env):
+        try:
+            r = subprocess.run([sys.executable, probe, "--workload", workload], env=dict(os.environ, **env), capture_output=True, text=True, timeout=180)
+            if r.returncode != 0:
+                return {"error": (r.stderr or r.stdout).strip().splitlines()[-1][:300] if (r.stderr or r.stdout).strip() else "exit %d" % r.returncode}
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            d["bit_exact"] = d.pop("frame_fnv") == production_fnv
+            return d
+        except Exception as e:                                     # timeouts included
+            return {"error": repr(e)[:300]}
+    out["production"] = run("production", {})
+    out["fast_runs"] = run("fast_runs", {"VXRT_FAST_RUNS": "1"})
+    lib = None
+    try:
+        if shutil.which(os.environ.get("NVCC", "nvcc")):
+            lib = vx.build.build_variant("late_domain_check")
+            out["late_domain_check"] = run("late_domain_check", {"VXRT_LIB": lib})
+        else:
+            out["late_domain_check"] = {"error": "nvcc unavailable"}
+    except Exception as e:
+        out["late_domain_check"] = {"error": repr(e)[:300]}
+    finally:
+        if lib and os.path.exists(lib):
+            os.remove(lib)
     return out
 
 

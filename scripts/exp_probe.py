@@ -1,0 +1,49 @@
+"""One kernel experiment, timed and checked in a process of its own (bench.py's "experiments" object; also usable by hand).
+The environment selects the build: nothing (the production library), VXRT_FAST_RUNS=1 (ray.cuh FAST_RUNS), or
+VXRT_LIB=<variant library>.  Renders the benchmark workload like bench.py's timed loop (production kernel variants, L2 flushed
+between frames, CUDA events inside vxrt_render) and prints ONE JSON line: per-kernel and per-frame milliseconds and the
+FNV-1a-64 of the RGBA8 frame, which the caller compares with the production frame (bit-exactness).
+    python scripts/exp_probe.py [--workload C3ii_4k] [--frames 40]"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch                      # noqa: E402
+import voxel_rt_b200 as vx        # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="C3ii_4k")
+ap.add_argument("--frames", type=int, default=40)
+a = ap.parse_args()
+scene, res = a.workload.rsplit("_", 1)
+W, H = vx.scenes.RESOLUTIONS[res]
+ren = vx.Renderer(grid=vx.scenes.DEFAULT_GRID, width=W, height=H)
+ren.initVoxels(); ren.buildDepthField()
+assert vx.scenes.fnv1a64(ren.downloadGrid()) == 0x4c58cc4001a22afa
+frame = vx.scenes.frame_for(scene, W, H)
+stream = torch.cuda.ExternalStream(ren.stream_ptr())
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+ren.updateUniforms(frame)
+ren.setStats(False)
+for _ in range(60):
+    ren.draw()
+ren.sync()
+p, s, t = [], [], []
+for _ in range(a.frames):
+    with torch.cuda.stream(stream):
+        flush.fill_(1)
+    ren.draw()
+    x = ren.stats()
+    p.append(x["ms_primary"]); s.append(x["ms_shadow"]); t.append(x["ms_total"])
+rgba = ren.renderFrameHost(frame)
+out = {"lib": os.path.basename(vx.build.lib_path()), "fast_runs": os.environ.get("VXRT_FAST_RUNS") == "1", "workload": a.workload,
+       "frames": a.frames, "ms_primary": round(statistics.mean(p), 4), "ms_shade": round(statistics.mean(s), 4),
+       "ms_per_frame": round(statistics.mean(t), 4), "ms_per_frame_min": round(min(t), 4),
+       "frame_fnv": "%016x" % vx.scenes.fnv1a64(rgba)}
+del flush
+torch.cuda.synchronize()
+ren.close()
+print(json.dumps(out))
