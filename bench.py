@@ -609,6 +609,7 @@ def experiments(workload, production_fnv):
         if shutil.which(os.environ.get("NVCC", "nvcc")):
             lib = vx.build.build_variant("late_domain_check")
             out["late_domain_check"] = run("late_domain_check", {"VXRT_LIB": lib})
+            out["late_domain_check+fast_runs"] = run("late_domain_check+fast_runs", {"VXRT_LIB": lib, "VXRT_FAST_RUNS": "1"})
         else:
             out["late_domain_check"] = {"error": "nvcc unavailable"}
     except Exception as e:
