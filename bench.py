@@ -592,15 +592,22 @@ def experiments(workload, production_fnv):
     probe = os.path.join(ROOT, "scripts", "exp_probe.py")
     out = {"note": "not part of value / e2e; same workload, scripts/exp_probe.py, one process each", "production_frame_fnv": production_fnv}
 
+    state = {"timed_out": False}
+
     def run(label, env):
+        if state["timed_out"]:                                     # something systemic: do not spend more of the bench's time
+            return {"error": "skipped after an earlier probe timed out"}
         try:
-            r = subprocess.run([sys.executable, probe, "--workload", workload], env=dict(os.environ, **env), capture_output=True, text=True, timeout=180)
+            r = subprocess.run([sys.executable, probe, "--workload", workload], env=dict(os.environ, **env), capture_output=True, text=True, timeout=120)
             if r.returncode != 0:
                 return {"error": (r.stderr or r.stdout).strip().splitlines()[-1][:300] if (r.stderr or r.stdout).strip() else "exit %d" % r.returncode}
             d = json.loads(r.stdout.strip().splitlines()[-1])
             d["bit_exact"] = d.pop("frame_fnv") == production_fnv
             return d
-        except Exception as e:                                     # timeouts included
+        except subprocess.TimeoutExpired:
+            state["timed_out"] = True
+            return {"error": "probe timed out after 120 s"}
+        except Exception as e:
             return {"error": repr(e)[:300]}
     out["production"] = run("production", {})
     out["fast_runs"] = run("fast_runs", {"VXRT_FAST_RUNS": "1"})
