@@ -585,7 +585,8 @@ def extra_workloads(vx, ren, flush_l2, stream, torch, steps=10):
 def experiments(workload, production_fnv):
     """Kernel experiments that are NOT in the numbers above (off by default / separate libraries), each timed and
     checked in a process of its own by scripts/exp_probe.py after the measurements of this line are complete: the production
-    library through the same probe (the figure to compare with), ray.cuh FAST_RUNS, and the late-domain-check variant library.
+    library through the same probe (the figure to compare with), ray.cuh FAST_RUNS, and the variant libraries (late domain
+    check, jump prefetch).
     "bit_exact": the probe's frame has the fingerprint of the production frame.  Never raises: a failing experiment is a note."""
     import shutil
     import voxel_rt_b200 as vx
@@ -611,19 +612,21 @@ def experiments(workload, production_fnv):
             return {"error": repr(e)[:300]}
     out["production"] = run("production", {})
     out["fast_runs"] = run("fast_runs", {"VXRT_FAST_RUNS": "1"})
-    lib = None
-    try:
-        if shutil.which(os.environ.get("NVCC", "nvcc")):
-            lib = vx.build.build_variant("late_domain_check")
-            out["late_domain_check"] = run("late_domain_check", {"VXRT_LIB": lib})
-            out["late_domain_check+fast_runs"] = run("late_domain_check+fast_runs", {"VXRT_LIB": lib, "VXRT_FAST_RUNS": "1"})
-        else:
-            out["late_domain_check"] = {"error": "nvcc unavailable"}
-    except Exception as e:
-        out["late_domain_check"] = {"error": repr(e)[:300]}
-    finally:
-        if lib and os.path.exists(lib):
-            os.remove(lib)
+    for name in ("late_domain_check", "jump_prefetch"):            # variant libraries (voxel_rt_b200.build.VARIANTS), built here
+        lib = None
+        try:
+            if not shutil.which(os.environ.get("NVCC", "nvcc")):
+                out[name] = {"error": "nvcc unavailable"}
+                continue
+            lib = vx.build.build_variant(name)
+            out[name] = run(name, {"VXRT_LIB": lib})
+            if name == "late_domain_check":
+                out[name + "+fast_runs"] = run(name + "+fast_runs", {"VXRT_LIB": lib, "VXRT_FAST_RUNS": "1"})
+        except Exception as e:
+            out[name] = {"error": repr(e)[:300]}
+        finally:
+            if lib and os.path.exists(lib):
+                os.remove(lib)
     return out
 
 

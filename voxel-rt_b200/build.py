@@ -101,6 +101,7 @@ VARIANTS = {
     # default library stays exactly what was validated (scripts/gpu_exp_variant.sh times them, VXRT_LIB=... pytest -m gpu
     # runs the whole parity suite on one)
     "late_domain_check": ["-DVXRT_EXP_LATE_DOMAIN_CHECK"],
+    "jump_prefetch": ["-DVXRT_EXP_JUMP_PREFETCH"],          # primary rays prefetch the line the next jump is expected to land on
 }
 
 
