@@ -14,3 +14,7 @@ bash scripts/gpu_exp_variant.sh VXRT_FAST_RUNS=0 VXRT_FAST_RUNS=1
 python voxel-rt_b200/build.py late_domain_check | tail -1
 VXRT_LIB=$PWD/voxel-rt_b200/libvxrt_exp_late_domain_check.so python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 bash scripts/gpu_exp_variant.sh VXRT_FAST_RUNS=0 VXRT_LIB=voxel-rt_b200/libvxrt_exp_late_domain_check.so
+python voxel-rt_b200/build.py jump_prefetch | tail -1
+for v in "" "VXRT_FAST_RUNS=1" "VXRT_LIB=$PWD/voxel-rt_b200/libvxrt_exp_late_domain_check.so" "VXRT_LIB=$PWD/voxel-rt_b200/libvxrt_exp_jump_prefetch.so"; do
+  env $v python scripts/exp_probe.py | tee -a gpurun_out/exp_probe.jsonl | cut -c1-400
+done
