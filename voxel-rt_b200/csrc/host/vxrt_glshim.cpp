@@ -5,7 +5,7 @@
 // UNMODIFIED, headless, with their per-pixel work on the B200:
 //
 //   reference call (file:line)                                            here
-//   glShaderSource(fshader.glsl text)              render.cpp:147     -> grid extents + shader constants are read from
+//   glShaderSource(fshader.glsl text)              render.cpp:146     -> grid extents + shader constants are read from
 //                                                                        the source; a shader whose constants differ
 //                                                                        from what the kernels implement is refused
 //   glBufferData(SSBO, 100663296, voxels, ..)      render.cpp:201,368 -> vxrt_create (first time) + vxrt_upload_grid
@@ -14,10 +14,10 @@
 //   glGetUniformLocation / glUniform*              render.cpp:335-341,289-296,410 -> fields of a vxrt_frame
 //   glViewport(0,0,w,h)                            render.cpp:405     -> vxrt_resize before the next draw
 //   glDrawArrays(GL_TRIANGLES,0,6)                 main.cpp:59        -> vxrt_set_frame + vxrt_render
-//   glfwSwapBuffers                                window.cpp:175     -> vxrt_sync (+ optional PPM of chosen frames)
-//   glfwPollEvents                                 window.cpp:176     -> scripted input through the reference's own
+//   glfwSwapBuffers                                window.cpp:174     -> vxrt_sync (+ optional PPM of chosen frames)
+//   glfwPollEvents                                 window.cpp:175     -> scripted input through the reference's own
 //                                                                        callbacks (keys, mouse, resize)
-//   glfwWindowShouldClose                          window.cpp:162,178 -> true after VXRT_GLSHIM_FRAMES presented frames
+//   glfwWindowShouldClose                          window.cpp:161,177 -> true after VXRT_GLSHIM_FRAMES presented frames
 //
 // No GL header is needed: the GL / GLFW ABI types are spelled out below (GLenum = unsigned int, ...).
 // There is no CPU path: if libvxrt cannot create its context (no sm_100 device) the process exits with the message.
@@ -32,7 +32,7 @@
 //                                 (+ "<file>.frame": the 360 bytes of that frame's vxrt_frame, to replay it elsewhere)
 //   VXRT_GLSHIM_DUMP_FRAMES=a,b   counted frames to dump (default: the last one)
 //   VXRT_GLSHIM_SAVE_GRID=path    when the window closes, stream the device grid into a VXRTGRD1 file (vxrt_save_grid)
-//   VXRT_GLSHIM_FPS=F             deterministic time: clock() advances CLOCKS_PER_SEC/F per frame (window.cpp:165 derives
+//   VXRT_GLSHIM_FPS=F             deterministic time: clock() advances CLOCKS_PER_SEC/F per frame (window.cpp:164 derives
 //                                 `fps` from clock(); movement, gravity and the sun depend on it).  Unset: real clock.
 //   VXRT_GLSHIM_DEVICE=D          CUDA device ordinal (default 0)
 //   VXRT_GLSHIM_LOG=1             one summary line on stderr when the window closes
@@ -482,7 +482,7 @@ int glfwWindowShouldClose(GLFWwindow*) {
     return close;
 }
 
-// ---- deterministic time (only with VXRT_GLSHIM_FPS): window.cpp:165 computes fps = CLOCKS_PER_SEC / (clock() - start) --
+// ---- deterministic time (only with VXRT_GLSHIM_FPS): window.cpp:164 computes fps = CLOCKS_PER_SEC / (clock() - start) --
 clock_t clock(void) noexcept {
     if (fixed_fps() > 0) return s_vclock;
     static clock_t (*real_clock)(void) = (clock_t(*)(void))dlsym(RTLD_NEXT, "clock");
