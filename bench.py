@@ -260,8 +260,13 @@ def run_b200(args):
         if nwarm % 16 == 15:
             ren.sync()
     barrier()
-    st = ren.stats()                                              # ray / fetch counts of this frame (counters on)
-    ren.setStats(False)                                           # production frames: no per-iteration counters
+    # ray / fetch counts of the frame, from the counted kernel variants (untimed): by the reference's casting rule (mode 1: every
+    # ray fshader.glsl casts, marched to its end) and of what the production kernels actually execute (mode 2)
+    ren.setStats(1); flush_l2(); step_device(); barrier(); st = ren.stats()
+    ren.setStats(2); flush_l2(); step_device(); barrier(); st_exec = ren.stats()
+    if args.no_cull:
+        st_exec = st
+    ren.setStats(0)                                               # production frames: no per-iteration counters
     for nwarm in range(3):
         flush_l2(); step_device()
     barrier()
@@ -290,15 +295,22 @@ def run_b200(args):
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-        cnt = torch.tensor([rays_local_rank, st["fetches"], st["hit_pixels"], st["rays_primary"], st["rays_global"], st["rays_local"]],
-                           dtype=torch.int64, device="cuda")
+        cnt = torch.tensor([rays_local_rank, st["fetches"], st["hit_pixels"], st["rays_primary"], st["rays_global"], st["rays_local"],
+                            st["rays_dark"], st_exec["rays_global"], st_exec["rays_local"], st_exec["fetches"], st["fetches_primary"],
+                            st_exec["fetches_primary"]], dtype=torch.int64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        rays, fetches, hits, rp, rg, rl = (int(x) for x in cnt.tolist())
+        rays, fetches, hits, rp, rg, rl, dark, rg_x, rl_x, fetches_x, fetches_p, fetches_px = (int(x) for x in cnt.tolist())
     else:
         rays, fetches, hits = rays_local_rank, st["fetches"], st["hit_pixels"]
-        rp, rg, rl = st["rays_primary"], st["rays_global"], st["rays_local"]
+        rp, rg, rl, dark = st["rays_primary"], st["rays_global"], st["rays_local"], st["rays_dark"]
+        rg_x, rl_x, fetches_x = st_exec["rays_global"], st_exec["rays_local"], st_exec["fetches"]
+        fetches_p, fetches_px = st["fetches_primary"], st_exec["fetches_primary"]
+    rays_traced = rp + rg_x + rl_x                               # rays the timed kernels trace (unlit rays are not cast)
     ms_per_step = total_ms / args.steps
-    value = rays / (ms_per_step * 1e-3) / 1e6                    # Mrays/s, whole job
+    # Mrays/s, whole job.  The headline counts only rays the timed kernels TRACE; the same time with the reference's ray count
+    # (every ray fshader.glsl casts for this frame, incl. the unlit ones whose term is exactly 0) is reported beside it
+    value = rays_traced / (ms_per_step * 1e-3) / 1e6
+    value_ref_rule = rays / (ms_per_step * 1e-3) / 1e6
 
     # ---- e2e: the public C-ABI call with HOST buffers (frame params in, RGBA8 frame out), wall clock ----
     host_out = ren.hostFrameBuffer()                              # page-locked (vxrt_host_alloc)
@@ -339,6 +351,13 @@ def run_b200(args):
         t0 = time.perf_counter()
         step_e2e()
         e2e_sync_s += time.perf_counter() - t0
+    # the frame the public call just delivered to host memory (and, where edits / the terrain generator made it, the grid it
+    # was rendered from): checked against the oracle after all timing is done ("parity" in the JSON line)
+    parity_frame = parity_level = None
+    if rank == 0 and not args.no_extra:
+        parity_frame = np.array(host_out if world == 1 else final_host.numpy(), copy=True).reshape(H, W, 4)
+        if scene in ("C4", "C5"):
+            parity_level = ren.downloadGrid()
     # (c) N > 1, frames straight to host memory: no exchange at all -- the kernels of every rank store their tiles' pixels
     # into ONE raster in shared page-locked host memory, each GPU over its own PCIe link; two host frames alternate and
     # rank 0 takes frame k (completion flags of all ranks) while frame k + 1 renders.  Returns False (and the caller
@@ -469,9 +488,10 @@ def run_b200(args):
             t = torch.tensor([t_nc], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             t_nc = float(t.item())
-        nocull = {"ms_per_step": round(t_nc / args.steps, 4), "value": round(rays / (t_nc / args.steps * 1e-3) / 1e6, 2), "unit": "Mrays/s"}
+        nocull = {"ms_per_step": round(t_nc / args.steps, 4), "value": round(rays / (t_nc / args.steps * 1e-3) / 1e6, 2), "unit": "Mrays/s",
+                  "rays_per_frame": rays}
         ren.setCulling(True)
-    e2e_value = rays / (e2e_s / args.steps) / 1e6
+    e2e_value = rays_traced / (e2e_s / args.steps) / 1e6
     clocks = sampler.stop()
     h2d = 360                                                     # the frame parameters (kernel arguments)
     d2h = W * H * 4                                               # the RGBA8 frame (rank 0)
@@ -481,39 +501,67 @@ def run_b200(args):
         hbm, peak_src = peaks()
         # dominant kernel = the one with the larger share of the frame
         prim_ms, shade_ms = statistics.mean(kern_ms["primary"]), statistics.mean(kern_ms["shade"])
-        fp = st["fetches_primary"]; fs = st["fetches"] - fp
-        bytes_primary = 4 * fp + 4 * st["rays_primary"] + 360                           # fetches + RGBA8/hit-record store
-        bytes_shade = 4 * fs + 4 * st["hit_pixels"] + 4 * st["hit_pixels"]              # fetches + colour read + RGBA8 store
+        # rank 0's kernels against rank 0's own work.  HBM bookkeeping: algorithmic bytes = 4 B x castRay iterations +
+        # colour read + RGBA8 / hit-record store; stated with the iterations the kernels EXECUTE (achieved / frac) and with the
+        # reference's iteration count for the same frame (every ray marched to its end), both named.
+        def alg_bytes(stx):
+            fpx = stx["fetches_primary"]; fsx = stx["fetches"] - fpx
+            return 4 * fpx + 4 * st["rays_primary"] + 360, 4 * fsx + 4 * st["hit_pixels"] + 4 * st["hit_pixels"]
+        bytes_primary, bytes_shade = alg_bytes(st_exec)
+        bytes_primary_ref, bytes_shade_ref = alg_bytes(st)
         dom = "shade_kernel" if shade_ms >= prim_ms else "primary_kernel"
-        dom_ms, dom_bytes = (shade_ms, bytes_shade) if dom == "shade_kernel" else (prim_ms, bytes_primary)
+        dom_ms, dom_bytes, dom_bytes_ref = (shade_ms, bytes_shade, bytes_shade_ref) if dom == "shade_kernel" else (prim_ms, bytes_primary, bytes_primary_ref)
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        # DRAM traffic per launch of that kernel from the committed ncu capture of this workload (profiles/), else null
-        traffic, ncu_extra = None, None
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
-            if prof.get("workload") == args.workload and world == 1:
-                kk = prof["kernels"][dom]
-                traffic = int(kk["dram_bytes_read"] + kk["dram_bytes_write"])
-                ncu_extra = {"source": "profiles/r1_ncu_traffic.json", "issue_slot_utilisation_pct": kk["issue_active_pct"],
+        achieved_ref = dom_bytes_ref / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        # ncu capture of this workload's kernels committed under profiles/ (scripts/ncu_summary.py): DRAM traffic per launch and the
+        # issue-slot figures -- the resource that actually binds these kernels
+        traffic, issue = None, None
+        for prof_name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+            try:
+                prof = json.load(open(os.path.join(ROOT, "profiles", prof_name)))
+                if prof.get("workload") == args.workload and world == 1:
+                    kk = prof["kernels"][dom]
+                    traffic = int(kk["dram_bytes_read"] + kk["dram_bytes_write"])
+                    it_exec = (st_exec["fetches"] - st_exec["fetches_primary"]) if dom == "shade_kernel" else st_exec["fetches_primary"]
+                    thread_inst = kk["warp_inst"] * kk["avg_active_threads_per_inst"]
+                    issue = {"bound": "issue", "kernel": dom, "source": "profiles/" + prof_name + (" (round-1 kernels: stale)" if prof_name.startswith("r1") else ""),
+                             "issue_slot_utilisation_pct": kk["issue_active_pct"], "frac": round(kk["issue_active_pct"] / 100.0, 4),
+                             "warp_instructions_per_launch": int(kk["warp_inst"]),
                              "avg_active_threads_per_instruction": kk["avg_active_threads_per_inst"],
-                             "achieved_occupancy_pct": kk["achieved_occupancy_pct"], "l1_hit_pct": kk["l1_hit_pct"], "l2_hit_pct": kk["l2_hit_pct"]}
-        except Exception:
-            pass
+                             "executed_iterations_per_launch": int(it_exec),
+                             "thread_instructions_per_executed_iteration": round(thread_inst / it_exec, 2) if it_exec else None,
+                             "achieved_occupancy_pct": kk["achieved_occupancy_pct"], "l1_hit_pct": kk["l1_hit_pct"], "l2_hit_pct": kk["l2_hit_pct"],
+                             "dram_bytes_over_algorithmic_bytes": round(traffic / dom_bytes, 4) if dom_bytes else None}
+                    break
+            except Exception:
+                continue
         roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s",
-                    "frac": round(achieved / hbm, 5), "traffic": traffic, "ncu": ncu_extra, "peak_source": peak_src,
-                    "note": "algorithmic bytes = 4 B x castRay iterations + colour read + RGBA8 store per launch (rank 0's tiles); "
-                            "the gathers are served by L1/L2 (DRAM traffic is a few % of the algorithmic bytes) and the kernels are bound by instruction issue, see DESIGN.md",
-                    "kernels": {"primary_kernel": {"ms": round(prim_ms, 4), "alg_bytes": int(bytes_primary)},
-                                "shade_kernel": {"ms": round(shade_ms, 4), "alg_bytes": int(bytes_shade)}}}
+                    "frac": round(achieved / hbm, 5), "traffic": traffic, "peak_source": peak_src,
+                    "achieved_with_reference_iterations": round(achieved_ref, 2), "frac_with_reference_iterations": round(achieved_ref / hbm, 5),
+                    "issue": issue,
+                    "note": "HBM bookkeeping figure: algorithmic bytes (4 B x castRay iterations the kernel executes + colour read + RGBA8 store, rank 0's "
+                            "tiles) / the kernel's CUDA-event time / measured copy peak.  The gathers are served by L1/L2 (DRAM traffic is a few % of the "
+                            "algorithmic bytes): the binding resource is instruction issue, reported in 'issue' from the committed ncu capture",
+                    "kernels": {"primary_kernel": {"ms": round(prim_ms, 4), "alg_bytes": int(bytes_primary), "alg_bytes_reference_iterations": int(bytes_primary_ref)},
+                                "shade_kernel": {"ms": round(shade_ms, 4), "alg_bytes": int(bytes_shade), "alg_bytes_reference_iterations": int(bytes_shade_ref)}}}
         result = {
             "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "value_counts": "rays the timed kernels trace (primary + lit global + lit local); see value_reference_casting_rule / value_all_rays_marched",
+            "value_reference_casting_rule": round(value_ref_rule, 2),
+            "value_all_rays_marched": None,
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (reference procedural default level, fnv1a64 %s; fixed camera)" % level_fnv,
             "config": {"workload": args.workload, "grid": list(grid), "width": W, "height": H, "local_lights": 16 if scene != "C1" else 0,
                        "setup": build_info,
-                       "view_depth_field": int(frame.view_depth_field), "rays_per_frame": rays, "rays_primary": rp, "rays_global": rg,
+                       "view_depth_field": int(frame.view_depth_field),
+                       "rays_traced_per_frame": rays_traced, "rays_traced": {"primary": rp, "global": rg_x, "local": rl_x},
+                       "iterations_executed_per_frame": fetches_x,
+                       "rays_per_frame": rays, "rays_primary": rp, "rays_global": rg,
                        "rays_local": rl, "voxel_fetches_per_frame": fetches, "hit_pixels": hits,
-                       "rays_facing_away_from_their_light": int(st["rays_dark"]),
+                       "rays_facing_away_from_their_light": dark,
+                       "counts": "rays_per_frame / rays_global / rays_local / voxel_fetches_per_frame follow the reference's casting rule (counted kernel "
+                                 "variants, every ray marched to its end); rays_traced* / iterations_executed* are what the timed production kernels do; "
+                                 "all summed over ranks",
                        "partition": "sort-first 32x8 tiles, tile t -> rank t %% %d, grid replicated; frame exchange: %s" % (
                            world, "none (1 GPU)" if world == 1 else ("kernels store into rank 0's frame over NVLink peer memory, release/acquire flags" if use_p2p
                                                                      else "NCCL all-gather of RGBA8 tiles + un-tile kernel")),
@@ -532,6 +580,11 @@ def run_b200(args):
             "wall_s_timed_region": round(t_wall, 3),
             "without_miss_culling": nocull,
         }
+        if nocull:
+            result["value_all_rays_marched"] = nocull["value"]
+        if parity_frame is not None:
+            result["parity"] = parity_check(frame, parity_frame, level_arr if parity_level is None else parity_level, grid, W, H,
+                                            stride=4 if scene != "C4" else 16)
         if scene == "C5":
             result["config"]["edits"] = "one vxrt_edit_remove_sphere(r=7) per frame, centres from mt19937(12345); rays/fetches are those of the last frame"
         if not args.no_extra and world == 1 and scene not in ("C4", "C5"):
@@ -554,6 +607,33 @@ def run_b200(args):
     ren.close()
     if rank == 0:
         print(json.dumps(result))
+
+
+def parity_check(frame_vx, got, level, dims, W, H, stride):
+    """The frame the timed public call delivered (host memory) against the oracle (oracle/vxo.c, the checker) on every
+    `stride`-th block of 8 rows, rendered from the same grid and frame parameters.  Bit-exact or it says how many pixels differ."""
+    try:
+        import voxel_rt_b200 as vx
+        ol, o = oracle_handle()
+        fr = ol.Frame()
+        C.memmove(C.byref(fr), C.byref(frame_vx), C.sizeof(fr))
+        blocks = [b for b in range((H + 7) // 8) if b % stride == 0]
+        bad, nrows = 0, 0
+        want_rows, got_rows = [], []
+        for b in blocks:
+            y0, y1 = b * 8, min(H, b * 8 + 8)
+            ref = o.render(level, tuple(dims), fr, W, H, y0=y0, y1=y1)["rgba8"][y0:y1]
+            bad += int((ref != got[y0:y1]).any(axis=2).sum())
+            nrows += y1 - y0
+            want_rows.append(ref); got_rows.append(got[y0:y1])
+        return {"rows": nrows, "of_rows": H, "pixels_checked": nrows * W, "mismatched_pixels": bad,
+                "oracle_rows_fnv": "%016x" % vx.scenes.fnv1a64(np.concatenate(want_rows)),
+                "frame_rows_fnv": "%016x" % vx.scenes.fnv1a64(np.concatenate(got_rows)),
+                "frame_fnv": "%016x" % vx.scenes.fnv1a64(got),
+                "what": "RGBA8 frame delivered to host memory by the e2e call (production kernels) vs oracle/vxo.c on every %d%s block of 8 rows, "
+                        "same grid and frame parameters; bit-exact comparison" % (stride, "th")}
+    except Exception as e:                                         # the checker must never take the bench line down
+        return {"error": repr(e)[:300]}
 
 
 def extra_workloads(vx, ren, flush_l2, stream, torch, steps=10):
@@ -583,10 +663,9 @@ def extra_workloads(vx, ren, flush_l2, stream, torch, steps=10):
 
 
 def experiments(workload, production_fnv):
-    """Kernel experiments that are NOT in the numbers above (off by default / separate libraries), each timed and
-    checked in a process of its own by scripts/exp_probe.py after the measurements of this line are complete: the production
-    library through the same probe (the figure to compare with), ray.cuh FAST_RUNS, and the variant libraries (late domain
-    check, jump prefetch).
+    """Kernel experiments that are NOT in the numbers above (separate variant libraries, voxel_rt_b200.build.VARIANTS), each timed
+    and checked in a process of its own by scripts/exp_probe.py after the measurements of this line are complete, beside the
+    production library through the same probe (the figure to compare with).
     "bit_exact": the probe's frame has the fingerprint of the production frame.  Never raises: a failing experiment is a note."""
     import shutil
     import voxel_rt_b200 as vx
@@ -611,8 +690,8 @@ def experiments(workload, production_fnv):
         except Exception as e:
             return {"error": repr(e)[:300]}
     out["production"] = run("production", {})
-    out["fast_runs"] = run("fast_runs", {"VXRT_FAST_RUNS": "1"})
-    for name in ("late_domain_check", "jump_prefetch"):            # variant libraries (voxel_rt_b200.build.VARIANTS), built here
+    import voxel_rt_b200 as vx
+    for name in sorted(vx.build.VARIANTS):                         # variant libraries (voxel_rt_b200.build.VARIANTS), built here
         lib = None
         try:
             if not shutil.which(os.environ.get("NVCC", "nvcc")):
@@ -620,8 +699,6 @@ def experiments(workload, production_fnv):
                 continue
             lib = vx.build.build_variant(name)
             out[name] = run(name, {"VXRT_LIB": lib})
-            if name == "late_domain_check":
-                out[name + "+fast_runs"] = run(name + "+fast_runs", {"VXRT_LIB": lib, "VXRT_FAST_RUNS": "1"})
         except Exception as e:
             out[name] = {"error": repr(e)[:300]}
         finally:
@@ -681,8 +758,9 @@ def run_frame_sharded(args):
         if nwarm % 16 == 15:
             ren.sync()
     barrier()
-    st = ren.stats()
-    ren.setStats(False)
+    ren.setStats(1); flush_l2(); ren.draw(); ren.sync(); st = ren.stats()       # counts by the reference's casting rule (untimed)
+    ren.setStats(2); flush_l2(); ren.draw(); ren.sync(); st_exec = ren.stats()  # what the production kernels trace
+    ren.setStats(0)
     for _ in range(3):
         flush_l2(); ren.draw()
     barrier()
@@ -715,13 +793,14 @@ def run_frame_sharded(args):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_s = (float(x) for x in t.tolist())
     clocks = sampler.stop()
-    rays = vx.scenes.total_rays(st)                                # per frame; every rank renders the same benchmark frame
+    rays_ref_rule = vx.scenes.total_rays(st)                       # per frame; every rank renders the same benchmark frame
+    rays = vx.scenes.total_rays(st_exec)                           # rays the timed kernels trace
     ms_per_step = total_ms / args.steps                            # one step = N frames, one per rank
     result = None
     if rank == 0:
         hbm, peak_src = peaks()
         prim_ms, shade_ms = statistics.mean(kern_ms["primary"]), statistics.mean(kern_ms["shade"])
-        fs = st["fetches"] - st["fetches_primary"]
+        fs = st_exec["fetches"] - st_exec["fetches_primary"]
         bytes_shade = 4 * fs + 8 * st["hit_pixels"]
         achieved = bytes_shade / (shade_ms * 1e-3) / 1e9 if shade_ms > 0 else 0.0
         result = {
@@ -730,7 +809,8 @@ def run_frame_sharded(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (reference procedural default level, fnv1a64 %s; fixed camera)" % level_fnv,
             "config": {"workload": args.workload, "grid": list(grid), "width": W, "height": H, "local_lights": 16 if scene != "C1" else 0,
-                       "rays_per_frame": rays, "frames_per_step": world, "voxel_fetches_per_frame": st["fetches"],
+                       "rays_traced_per_frame": rays, "rays_per_frame": rays_ref_rule, "frames_per_step": world, "voxel_fetches_per_frame": st["fetches"],
+                       "iterations_executed_per_frame": st_exec["fetches"],
                        "partition": "frame-sharded: rank r renders whole frames r, r+N, ... on its own grid replica, no exchange "
                                     "(opt-in; the default is BASELINE's sort-first tile split of one frame)",
                        "frame_latency_ms": round(ms_per_step, 4), "ms_per_frame_throughput": round(ms_per_step / world, 4),

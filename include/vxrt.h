@@ -166,10 +166,15 @@ int vxrt_set_culling(vxrt_ctx* ctx, int enabled);
 /* enabled (default): the primary pass records how long each tile's block took and the next frame launches the
    slowest tiles first (shorter kernel tail; it matters when a GPU renders only a fraction of the frame).  Same pixels. */
 int vxrt_set_tile_ordering(vxrt_ctx* ctx, int enabled);
-/* enabled (default): every vxrt_render maintains the fetch / local-ray counters of vxrt_stats.  Disabled: the
-   kernels skip the per-iteration counter (rays_local / fetches read back as 0; hit_pixels, rays_primary,
-   rays_global and the timings stay valid).  Same pixels either way. */
-int vxrt_set_stats(vxrt_ctx* ctx, int enabled);
+/* mode 0 (default) = the production kernels: no per-iteration counter, rays that cannot change a pixel are not traced
+   (vxrt_set_culling); vxrt_get_stats then reads rays_local / fetches / rays_dark as 0 while hit_pixels, rays_primary,
+   rays_global and the timings stay valid.  mode 1: every vxrt_render runs the counted kernel variants by the REFERENCE's
+   casting rule (every ray fshader.glsl casts is marched to its end and counted; rays_dark = how many of them face away from
+   their light; ~1.5x the frame time).  mode 2: counted variants that skip exactly what the production kernels skip:
+   rays_global / rays_local = rays traced, fetches = DDA iterations executed, rays_dark = rays not traced.  Same pixels in
+   every mode.  A debug context (VXRT_FLAG_DEBUG_OUTPUTS) counts by mode 1 unless mode 2 is set; the step-count view
+   always counts its primary rays. */
+int vxrt_set_stats(vxrt_ctx* ctx, int mode);
 /* set_frame + render + device->host copy of the RGBA8 frame into out (width*height*4 bytes) + sync.
    world > 1: out receives this rank's tiles in gather layout (vxrt_local_bytes()). */
 int vxrt_render_frame_host(vxrt_ctx* ctx, const vxrt_frame* frame, uint8_t* out);

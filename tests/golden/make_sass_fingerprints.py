@@ -36,7 +36,8 @@ def nvcc_version():
 
 
 if __name__ == "__main__":
-    fp = {"nvcc": nvcc_version(), "kernels": fingerprints()}
+    measured = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--measured=")]
+    fp = {"nvcc": nvcc_version(), "measured": measured[0] if measured else "not yet measured", "kernels": fingerprints()}
     if "--write" in sys.argv:
         with open(OUT, "w") as f:
             json.dump(fp, f, indent=1, sort_keys=True)

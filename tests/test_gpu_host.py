@@ -111,9 +111,6 @@ GAME = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
 
 
 @pytest.mark.skipif(not os.path.exists(GAME), reason="oracle/_ref/voxel_rt_on_vxrt not built (make -C oracle ref)")
-@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: its first run on a B200 is the round-end run itself. The game "
-                                         "is a separate process, so a failure cannot disturb the parity tests; the same session against an "
-                                         "oracle-backed mock libvxrt passes on the CPU (tests/test_glshim.py)")
 def test_reference_game_on_the_b200_through_the_gl_shim(vx, oracle, default_level, tmp_path):
     """oracle/_ref/voxel_rt_on_vxrt = the reference's six objects, unmodified, linked against libvxrt_glshim.so + libvxrt.so:
     its own main loop (main.cpp:47-75) with scripted input -- look down, place a light, right-click destruction (900

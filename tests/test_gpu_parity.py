@@ -170,6 +170,7 @@ def test_banded_readback_renders_the_same_frame(vx, oracle, default_level, size)
     want = oracle.render(default_level, gc.DIMS, fr, W, H)["rgba8"]
     with vx.Renderer(grid=gc.DIMS, width=W, height=H) as r:
         r.updateGeometry(default_level)
+        r.setStats(True)                                             # counted variants: the fetch counter is compared below
         pinned = r.hostFrameBuffer()
         for nb in (1, 2, 3, 4, 7, 16):
             r.setReadbackBands(nb)
@@ -483,12 +484,14 @@ def test_tile_partition_reassembles_the_frame(vx, default_level, world):
     fr = to_vx_frame(vx, gc.frame_cases(W, H)["C3ii_pitched"])
     with vx.Renderer(grid=gc.DIMS, width=W, height=H) as full:
         full.updateGeometry(default_level)
+        full.setStats(True)
         want = full.renderFrameHost(fr)
         st_full = full.stats()
     parts, tot = [], dict(rays_primary=0, rays_global=0, rays_local=0, fetches=0, hit_pixels=0)
     for rank in range(world):
         with vx.Renderer(grid=gc.DIMS, width=W, height=H, rank=rank, world=world) as r:
             r.updateGeometry(default_level)
+            r.setStats(True)
             parts.append(r.renderFrameHost(fr))
             st = r.stats()
             for k in tot:
@@ -695,10 +698,8 @@ def test_local_light_slots(vx):
 
 
 # ---- experiments (off by default in the library; their tests are gated until they have run on a B200 once) ------------
-@pytest.mark.xfail(strict=False, reason="ray.cuh FAST_RUNS experiment (off by default): written after round 1's GPU budget was spent, its first run on a "
-                                         "B200 is the round-end run.  It runs in a process of its own (new device code: a fault must not touch the "
-                                         "CUDA context of the parity tests); xpassed = the experiment is bit-exact on the real GPU")
 def test_fast_runs_experiment_in_a_subprocess():
+    """ray.cuh FAST_RUNS (off by default), in a process of its own; bit-exact on the B200 in round 1's final run"""
     out = run_variant_check("FAST_RUNS", VXRT_FAST_RUNS="1")
     assert "FAST_RUNS ok" in out
 
@@ -711,21 +712,6 @@ def run_variant_check(label, **env):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
     return r.stdout
-
-
-@pytest.mark.xfail(strict=False, reason="variant library libvxrt_exp_late_domain_check.so (ray.cuh VXRT_EXP_LATE_DOMAIN_CHECK: divide before the domain test, "
-                                         "so that the shade kernel stops computing the re-base dividends twice): written after round 1's GPU budget was "
-                                         "spent; built here with nvcc and checked in a process of its own; xpassed = bit-exact on the real GPU")
-def test_late_domain_check_variant_in_a_subprocess(vx):
-    import shutil
-    if not shutil.which(os.environ.get("NVCC", "nvcc")):
-        pytest.skip("nvcc unavailable")
-    lib = vx.build.build_variant("late_domain_check")
-    try:
-        out = run_variant_check("late_domain_check", VXRT_LIB=lib)
-        assert "late_domain_check ok" in out and os.path.basename(lib) in out
-    finally:
-        os.remove(lib)
 
 
 @pytest.mark.skipif(os.environ.get("VXRT_TEST_EXPERIMENTS") != "1",
@@ -767,3 +753,131 @@ def test_fast_runs_experiment_is_bit_exact(vx, oracle, golden, default_level, mo
         fr = gc.frame_cases(640, 360)["C2"]
         got = r.renderFrameHost(to_vx_frame(vx, fr))
         assert np.array_equal(got, oracle.render(default_level, gc.DIMS, fr, 640, 360)["rgba8"])
+
+
+# ---- the published configurations at the sizes bench.py publishes (BASELINE.json configs[2..4]) -----------------------
+def to_ol_frame(fr):
+    import ctypes as C
+    out = ol.Frame()
+    C.memmove(C.byref(out), C.byref(fr), C.sizeof(out))
+    return out
+
+
+@pytest.mark.parametrize("name", ["C2", "C3i", "C3ii_pitched"])
+def test_published_4k_frames_on_the_production_kernels(vx, oracle, default_level, name):
+    """BASELINE configs[2] at 3840x2160 ("C2" lights at 4K == workload C3ii_4k, the headline): a non-debug context with the
+    counters off runs exactly the kernels bench.py times (culling, unlit rays skipped, launch ordering from the second frame
+    on); every pixel of the 4K frame against the oracle, for the first frame and for a frame rendered with launch orders"""
+    W, H = 3840, 2160
+    fr = gc.frame_cases(W, H)[name]
+    want = oracle.render(default_level, gc.DIMS, fr, W, H)["rgba8"]
+    with vx.Renderer(grid=gc.DIMS, width=W, height=H) as r:
+        r.updateGeometry(default_level)
+        out = r.hostFrameBuffer()
+        for k in range(3):                                           # frame 0: no launch order yet; 1, 2: slowest-first orders
+            out[:] = 0x5A                                            # poison: a dropped tile cannot hide behind the last frame
+            r.renderFrameHost(to_vx_frame(vx, fr), out)
+            bad = int((out != want).any(axis=2).sum())
+            assert bad == 0, "%s frame %d: %d of %d pixels differ from the oracle" % (name, k, bad, W * H)
+        r.updateUniforms(to_vx_frame(vx, fr))
+        for k in range(2):                                           # vxrt_render (whole-frame launch, ordered) + read-back
+            r.draw()
+        assert np.array_equal(r.readPixels(), want)
+
+
+def test_c5_thousand_edits_match_the_reference_replay(vx, oracle, default_level):
+    """BASELINE configs[4]: 1000 right-click edits (controls.cpp:100-110 -> level.cpp:30-56) on the device grid, a 4K
+    production frame every 100 edits; grid fingerprint and frames against the oracle's replay of the same edits"""
+    W, H = 3840, 2160
+    edits = vx.scenes.edit_centres(1000)
+    fr = gc.frame_cases(W, H)["C3ii_pitched"]
+    level = default_level.copy()
+    with vx.Renderer(grid=gc.DIMS, width=W, height=H) as r:
+        r.updateGeometry(level)
+        out = r.hostFrameBuffer()
+        for k, c in enumerate(edits):
+            r.removeSphere(c, 7)
+            oracle.remove_sphere(level, gc.DIMS, int(c[0]), int(c[1]), int(c[2]), 7)
+            if k % 100 == 99:
+                out[:] = 0x5A
+                r.renderFrameHost(to_vx_frame(vx, fr), out)
+                want = oracle.render(level, gc.DIMS, fr, W, H)["rgba8"]
+                bad = int((out != want).any(axis=2).sum())
+                assert bad == 0, "after %d edits: %d pixels differ" % (k + 1, bad)
+        got = r.downloadGrid()
+    assert h64(oracle, got) == h64(oracle, level)
+
+
+def test_c4_terrain_1024_depth_field_and_frame_rows(vx, oracle):
+    """BASELINE configs[3]: the 1024^3 synthetic terrain generated and depth-fielded on the device (4 GiB).  The depth
+    field against the oracle's fixDepthField (render.cpp:226-253) on >= 10^5 sampled cells incl. every face of the grid
+    (only the SIGN of the neighbours enters, so the downloaded grid serves as input), the height field against the host
+    statement of the generator, then 96 rows of the 4K production frame against the oracle on the downloaded grid"""
+    import terrain_port
+    dims = vx.scenes.TERRAIN_GRID
+    W, H = 3840, 2160
+    w, h, d = dims
+    with vx.Renderer(grid=dims, width=W, height=H) as r:
+        r.generateTerrain(vx.scenes.TERRAIN_SEED)
+        r.buildDepthField()
+        level = r.downloadGrid()
+        surf = r.terrainHeight(w // 2, d // 2)
+        vfr = vx.scenes.terrain_frame(W, H, surf)
+        out = r.hostFrameBuffer()
+        out[:] = 0x5A
+        r.renderFrameHost(vfr, out)
+        got = np.array(out, copy=True)
+    g = level.reshape(d, h, w)
+    # generator: columns against the host statement (surface height, material bands)
+    rs = np.random.RandomState(4)
+    for _ in range(200):
+        x, z = int(rs.randint(0, w)), int(rs.randint(0, d))
+        s = terrain_port.height(vx.scenes.TERRAIN_SEED, x, z, h)
+        assert (g[z, :s + 1, x] >= 0).all() and g[z, h - 1, x] < 0       # solid up to the surface (trees only add solids above it)
+    # depth field: sampled cells, all six faces included
+    n = 120000
+    xs, ys, zs = rs.randint(0, w, n), rs.randint(0, h, n), rs.randint(0, d, n)
+    k = n // 12
+    xs[:k] = 0; xs[k:2 * k] = w - 1; ys[2 * k:3 * k] = 0; ys[3 * k:4 * k] = h - 1; zs[4 * k:5 * k] = 0; zs[5 * k:6 * k] = d - 1
+    near = slice(6 * k, 9 * k)                                        # cells close above the surface (where the values vary)
+    for i in range(near.start, near.stop):
+        ys[i] = min(h - 1, terrain_port.height(vx.scenes.TERRAIN_SEED, int(xs[i]), int(zs[i]), h) + 1 + int(rs.randint(0, 9)))
+    work = np.where(level < 0, np.int32(-1), level)                   # the level before the depth field (render.cpp:349-352: -1)
+    for x, y, z in zip(xs, ys, zs):
+        oracle.fix_depth_field(work, dims, int(x), int(y), int(z))
+    idx = xs.astype(np.int64) + w * ys.astype(np.int64) + w * h * zs.astype(np.int64)
+    bad = int((work[idx] != level[idx]).sum())
+    assert bad == 0, "%d of %d sampled depth-field cells differ from the oracle" % (bad, n)
+    del work
+    # frame: 12 blocks of 8 rows spread over the frame (sky, horizon, ground)
+    fr = to_ol_frame(vfr)
+    for b in range(12):
+        y0 = (b * 22 + 3) * 8
+        ref = oracle.render(level, dims, fr, W, H, y0=y0, y1=y0 + 8)["rgba8"]
+        assert np.array_equal(got[y0:y0 + 8], ref[y0:y0 + 8]), "rows %d..%d" % (y0, y0 + 8)
+
+
+def test_stats_modes_count_the_reference_rule_and_the_executed_work(vx, oracle, default_level):
+    """vxrt_set_stats: 1 = every ray the reference casts, marched to its end (== the oracle's counters); 2 = what the production
+    kernels execute (unlit rays not traced, certain misses cut short); 0 = no counters.  Same pixels in every mode."""
+    W, H = 640, 360
+    for name in ("C2", "C3ii_pitched", "low_sun"):
+        fr = gc.frame_cases(W, H)[name]
+        ref = oracle.render(default_level, gc.DIMS, fr, W, H)
+        with vx.Renderer(grid=gc.DIMS, width=W, height=H) as r:
+            r.updateGeometry(default_level)
+            frames, st = {}, {}
+            for mode in (0, 1, 2):
+                r.setStats(mode)
+                frames[mode] = r.renderFrameHost(to_vx_frame(vx, fr))
+                st[mode] = r.stats()
+                assert np.array_equal(frames[mode], ref["rgba8"]), (name, mode)
+            c = [int(x) for x in ref["counters"]]
+            assert (st[1]["rays_primary"], st[1]["rays_global"], st[1]["rays_local"], st[1]["fetches"], st[1]["hit_pixels"]) == tuple(c)
+            assert st[0]["fetches"] == 0 and st[0]["rays_local"] == 0 and st[0]["hit_pixels"] == c[4]
+            # mode 2: traced + skipped == the reference's rays; never more iterations than the reference
+            assert st[2]["rays_global"] + st[2]["rays_local"] + st[2]["rays_dark"] == st[1]["rays_global"] + st[1]["rays_local"]
+            assert st[2]["rays_dark"] == st[1]["rays_dark"] and 0 < st[2]["fetches"] < st[1]["fetches"]
+            assert st[2]["hit_pixels"] == c[4] and st[2]["rays_primary"] == c[0]
+            with pytest.raises(vx.VxrtError):
+                r.setStats(3)

@@ -29,5 +29,4 @@ def test_production_kernels_are_the_measured_ones(vx):
     assert set(got) == set(want["kernels"])
     changed = sorted(k for k in got if got[k] != want["kernels"][k])
     assert not changed, changed
-    production = [k for k in got if not is_experiment(k)]
-    assert len(production) == 27 and len(got) - len(production) == 5          # 4 shade + 1 known-answer variants of FAST_RUNS
+    assert want.get("measured"), "the fingerprint file names the profiles/ entry its kernels were measured in"

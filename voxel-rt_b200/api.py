@@ -354,9 +354,10 @@ class Renderer:
     def setTileOrdering(self, enabled):
         self._check(self.lib.vxrt_set_tile_ordering(self._h, 1 if enabled else 0))
 
-    def setStats(self, enabled):
-        """fetch / local-ray counters on (default) or off (production frames: one issue slot less per DDA iteration)"""
-        self._check(self.lib.vxrt_set_stats(self._h, 1 if enabled else 0))
+    def setStats(self, mode):
+        """0 / False (default): production kernels, no per-iteration counters; 1 / True: counted variants by the reference's
+        casting rule; 2: counted variants that skip what the production kernels skip (counts of executed work)"""
+        self._check(self.lib.vxrt_set_stats(self._h, int(mode)))
 
     def setReadbackBands(self, n):
         self._check(self.lib.vxrt_set_readback_bands(self._h, int(n)))

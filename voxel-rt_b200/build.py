@@ -98,10 +98,9 @@ def build(force=False, verbose=False):
 
 VARIANTS = {
     # name -> extra nvcc flags; experiments that change the SASS of the render kernels live behind macros so that the
-    # default library stays exactly what was validated (scripts/gpu_exp_variant.sh times them, VXRT_LIB=... pytest -m gpu
-    # runs the whole parity suite on one)
-    "late_domain_check": ["-DVXRT_EXP_LATE_DOMAIN_CHECK"],
-    "jump_prefetch": ["-DVXRT_EXP_JUMP_PREFETCH"],          # primary rays prefetch the line the next jump is expected to land on
+    # default library stays exactly what was validated (VXRT_LIB=... pytest -m gpu runs the whole parity suite on one;
+    # bench.py's "experiments" object times every entry).  Round 1's late_domain_check is the default now, jump_prefetch
+    # (a measured loss) is gone.
 }
 
 

@@ -34,7 +34,7 @@ struct TileMap {
 
 struct Counters {
     unsigned int hit_count;
-    unsigned int pad;
+    unsigned int global_traced;         // counted variants: global-light rays actually traced (== hit_count unless unlit rays are skipped)
     unsigned long long rays_local, fetches_primary, fetches_shadow;
     unsigned long long rays_dark;       // shadow / light rays whose surface faces away from the light (cannot change the pixel)
 };
@@ -42,7 +42,8 @@ struct Counters {
 struct Outputs {
     uint32_t* rgba8;                    // raster [height][width] (world==1 or peer-memory target); else tile-compact [nlocal][8][32]
     int raster;                         // 1: rgba8 is a raster frame
-    int skip_dark;                      // production frames: do not trace rays whose outcome cannot change the pixel (N.L <= 0)
+    int skip_dark;                      // do not trace rays whose outcome cannot change the pixel (N.L <= 0): production frames, and the
+                                        // counted variants under vxrt_set_stats(2) (count what the production kernels execute)
     float4* hitq;                       // per local tile, 256 slots: hitPos.xyz, w = colour(24) | normal(4)<<24 of the tile's hit pixels, compacted
     uint32_t* hitpix;                   // raster pixel id of each entry
     uint32_t* tile_hits;                // per local tile: number of entries
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_cons
     }
     __syncthreads();
     const unsigned i = (unsigned)tile * TILE_PIX + (unsigned)slot;
-    unsigned fetches = 0, nlocal = 0, ndark = 0;
+    unsigned fetches = 0, nlocal = 0, ndark = 0, nglobal = 0;
     if ((unsigned)slot < count) {
         const float4 rec = o.hitq[i];
         const uint32_t pid = o.hitpix[i];
@@ -230,8 +231,9 @@ __global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_cons
         // Rays toward a light the surface faces away from (N.L <= 0) add exactly +-0 to the multiplier whether they
         // are occluded or not (fshader.glsl:155,177: "* max(0, dot(N, L))"), so production frames do not trace them; the
         // sign test uses the unnormalised direction (normalising multiplies by a positive number).  Counted variants
-        // (statistics / debug planes) trace every ray the reference casts and report how many were of this kind.
-        const bool skip_dark = !COUNT && o.skip_dark != 0;
+        // (statistics / debug planes) trace every ray the reference casts and report how many were of this kind, unless
+        // the host asks them to count what the production kernels execute (skip_dark set: rays_dark = rays skipped).
+        const bool skip_dark = o.skip_dark != 0;
         // :147
         float lx = __fsub_rn(f.light_pos[0], hx), ly = __fsub_rn(f.light_pos[1], hy), lz = __fsub_rn(f.light_pos[2], hz);
         const bool g_lit = dot3(nx, ny, nz, lx, ly, lz) > 0.0f;
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_cons
         uint32_t occl = 0u, cast = 1u;
         if (COUNT && !g_lit) ndark++;
         if (g_lit || !skip_dark) {   // :154 global-light shadow ray
+            if (COUNT) nglobal++;
             normalize3(lx, ly, lz);
             const RayHit s = cast_ray<COUNT, true, true, Grid, FAST>(g, __fadd_rn(hx, __fmul_rn(lx, 0.001f)), __fadd_rn(hy, __fmul_rn(ly, 0.001f)),
                                       __fadd_rn(hz, __fmul_rn(lz, 0.001f)), lx, ly, lz, VXRT_RENDER_DIST);
@@ -260,12 +263,12 @@ __global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_cons
             float tx = __fsub_rn(L.x, hx), ty = __fsub_rn(L.y, hy), tz = __fsub_rn(L.z, hz);
             // (a non-finite weight would turn the +-0 into NaN: such a light is always traced)
             const bool lit = dot3(nx, ny, nz, tx, ty, tz) > 0.0f || !(fabsf(L.w) <= 3.0e38f);
-            if (skip_dark && !lit) continue;
+            if (!COUNT && skip_dark && !lit) continue;
             const float lld = __fsqrt_rn(dot3(tx, ty, tz, tx, ty, tz));                      // :168
             if (lld <= (float)VXRT_LOCAL_LIGHT_DIST) {                                       // :171
+                if (COUNT && !lit) { ndark++; if (skip_dark) continue; }
                 normalize3_with_length(tx, ty, tz, lld);                                    // :173 (same dot, same sqrt as :168)
                 cast |= 2u << slot; nlocal++;
-                if (COUNT && !lit) ndark++;
                 const RayHit s = cast_ray<COUNT, true, false, Grid, FAST>(g, __fadd_rn(hx, __fmul_rn(tx, 0.001f)), __fadd_rn(hy, __fmul_rn(ty, 0.001f)),
                                           __fadd_rn(hz, __fmul_rn(tz, 0.001f)), tx, ty, tz, f2i(__fadd_rn(lld, 1.0f)));   // :175
                 fetches += (unsigned)s.steps;
@@ -287,8 +290,9 @@ __global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_cons
     }
     const unsigned wf = __reduce_add_sync(0xffffffffu, fetches), wl = __reduce_add_sync(0xffffffffu, nlocal);
     if (COUNT) {
-        const unsigned wd = __reduce_add_sync(0xffffffffu, ndark);
+        const unsigned wd = __reduce_add_sync(0xffffffffu, ndark), wg = __reduce_add_sync(0xffffffffu, nglobal);
         if (lane == 0 && wd) atomicAdd(&o.counters->rays_dark, (unsigned long long)wd);
+        if (lane == 0 && wg) atomicAdd(&o.counters->global_traced, wg);
     }
     if (lane == 0 && wf) { atomicAdd(&s_fetches, (unsigned long long)wf); atomicAdd(&s_local, (unsigned long long)wl); }
     __syncthreads();

@@ -102,7 +102,9 @@ struct vxrt_ctx {
     size_t p2p_frame_bytes = 0;
     unsigned long long p2p_seq = 0;     // frames rendered into the target so far
     int* d_p2p_err = nullptr;
-    bool count_stats = true;            // vxrt_set_stats: maintain fetch / local-ray counters (costs ~1 issue slot per DDA iteration)
+    int stats_mode = 0;                 // vxrt_set_stats: 0 = production kernels (no per-iteration counters); 1 = counted variants, every ray
+                                        // the reference casts is marched to its end (ray / fetch counts by the reference's casting rule);
+                                        // 2 = counted variants that skip what the production kernels skip (counts of what is executed)
     uint32_t launches = 0;
 };
 
@@ -123,7 +125,11 @@ static GridView grid_view(const vxrt_ctx* c) {
     g.vox = c->d_vox; g.w = c->cfg.grid_w; g.h = c->cfg.grid_h; g.d = c->cfg.grid_d;
     g.wh = g.w * g.h; g.n = g.w * g.h * g.d;
     g.ymin = c->yrange[0]; g.ymax = c->yrange[1];
-    if (!c->use_culling) { g.ymin = INT_MIN / 2; g.ymax = INT_MAX / 2; }      // "every row may hold a solid": nothing is ever culled
+    // "every row may hold a solid": nothing is ever culled -- culling switched off, or counted variants that follow the
+    // reference's casting rule (stats mode 1, debug planes)
+    const bool counted_full = c->stats_mode == 1 || (c->stats_mode == 0 && c->d_dbg_hit != nullptr);
+    // (the step-count view shows the number of iterations: its rays always march to their end)
+    if (!c->use_culling || counted_full || c->frame.view_depth_field == 1) { g.ymin = INT_MIN / 2; g.ymax = INT_MAX / 2; }
     return g;
 }
 
@@ -219,7 +225,7 @@ static int ensure_stage(vxrt_ctx* c, size_t elems, size_t rows) {
 // occupancy summary used by cast_ray's CULL: expand (or, reset = true, recompute) the range of rows with solid voxels
 // from the device grid's linear range [first, first+count)
 static int update_yrange(vxrt_ctx* c, size_t first, size_t count, bool reset) {
-    if (!c->d_yrange) CUDA_TRY(cudaMalloc(&c->d_yrange, 2 * sizeof(int)));
+    if (!c->d_yrange) CUDA_TRY(cudaMalloc(&c->d_yrange, 4 * sizeof(int)));      // [0..1] the range, [2] sink of the L2 sweep
     if (reset) { c->yrange[0] = INT_MAX; c->yrange[1] = INT_MIN; }
     CUDA_TRY(cudaMemcpyAsync(c->d_yrange, c->yrange, 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     if (count) {
@@ -689,7 +695,8 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
     memcpy(&fp, &c->frame, sizeof fp);
     // kernel variants: iteration counting on/off (the step-count view and the debug planes always need it), and the
     // reference's compile-time grid extents (512 x 96 x 512) vs runtime extents
-    const bool count = c->count_stats || c->d_dbg_hit != nullptr;
+    const bool count = c->stats_mode != 0 || c->d_dbg_hit != nullptr;
+    const bool counted_full = c->stats_mode == 1 || (c->stats_mode == 0 && c->d_dbg_hit != nullptr);
     const bool count_primary = count || c->frame.view_depth_field == 1;
     const bool ref_dims = (g.w == GridViewRef::w && g.h == GridViewRef::h && g.d == GridViewRef::d);
     GridViewRef gr; gr.vox = g.vox; gr.ymin = g.ymin; gr.ymax = g.ymax;
@@ -713,11 +720,11 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
     if (sweep && (size_t)c->nvox * 4 <= (size_t)120 << 20) {              // only grids that fit the 126 MB L2
         // rows a ray can read: up to 7 above the highest solid row (beyond that the culling ends the ray), all rows otherwise
         int ytop = c->cfg.grid_h;
-        if (c->use_culling && !count && c->yrange[1] >= c->yrange[0]) ytop = std::min(c->cfg.grid_h, c->yrange[1] + 9);
+        if (c->use_culling && !counted_full && c->yrange[1] >= c->yrange[0]) ytop = std::min(c->cfg.grid_h, c->yrange[1] + 9);
         const int slab_ints = c->cfg.grid_w * c->cfg.grid_h;
         const int lines_per_slab = (c->cfg.grid_w * ytop + 31) / 32;
         const long long nlines = (long long)lines_per_slab * c->cfg.grid_d;
-        l2_prefetch_kernel<<<148 * 8, 256, 0, c->stream>>>(c->d_vox, lines_per_slab, slab_ints, nlines, (int*)&c->d_counters[MAX_BANDS - 1].pad);
+        l2_prefetch_kernel<<<148 * 8, 256, 0, c->stream>>>(c->d_vox, lines_per_slab, slab_ints, nlines, c->d_yrange ? c->d_yrange + 2 : nullptr);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
     }
@@ -740,7 +747,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         Outputs o;
         o.rgba8 = p2p_frame ? (uint32_t*)(c->p2p_base + sizeof(P2PShared) + (c->p2p_seq & 1) * c->p2p_frame_bytes) : dev_out;
         o.raster = (c->cfg.world == 1 || p2p_frame || raster_out) ? 1 : 0;
-        o.skip_dark = c->use_culling ? 1 : 0;
+        o.skip_dark = (c->use_culling && !counted_full) ? 1 : 0;
         o.hitq = c->d_hitq; o.hitpix = c->d_hitpix; o.tile_hits = c->d_tile_hits;
         o.counters = c->d_counters + b;
         // longest-tile-first launch order (whole-frame launches only; bands keep their contiguous tile ranges)
@@ -862,7 +869,8 @@ extern "C" int vxrt_set_tile_ordering(vxrt_ctx* c, int enabled) {
 
 extern "C" int vxrt_set_stats(vxrt_ctx* c, int enabled) {
     if (!c) return fail(VXRT_ERR_INVALID, "null context");
-    c->count_stats = enabled != 0;
+    if (enabled < 0 || enabled > 2) return fail(VXRT_ERR_INVALID, "set_stats: 0 off, 1 reference casting rule, 2 executed work");
+    c->stats_mode = enabled;
     return VXRT_OK;
 }
 
@@ -962,7 +970,7 @@ extern "C" int vxrt_get_stats(vxrt_ctx* c, vxrt_stats* out) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     memset(&h, 0, sizeof h);
     for (int b = 0; b < MAX_BANDS; b++) {
-        h.hit_count += hb[b].hit_count; h.rays_local += hb[b].rays_local;
+        h.hit_count += hb[b].hit_count; h.global_traced += hb[b].global_traced; h.rays_local += hb[b].rays_local;
         h.fetches_primary += hb[b].fetches_primary; h.fetches_shadow += hb[b].fetches_shadow; h.rays_dark += hb[b].rays_dark;
     }
     memset(out, 0, sizeof *out);
@@ -978,7 +986,7 @@ extern "C" int vxrt_get_stats(vxrt_ctx* c, vxrt_stats* out) {
     }
     out->rays_primary = pix;
     out->hit_pixels = h.hit_count;
-    out->rays_global = (c->frame.view_depth_field == 1) ? 0 : h.hit_count;
+    out->rays_global = (c->frame.view_depth_field == 1) ? 0 : (c->stats_mode == 2 ? h.global_traced : h.hit_count);
     out->rays_local = h.rays_local;
     out->fetches = h.fetches_primary + h.fetches_shadow;
     out->fetches_primary = h.fetches_primary;
