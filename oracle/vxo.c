@@ -6,6 +6,7 @@
  * order and int arithmetic wraps.  Citations are file:line under the reference's src/.
  */
 #include "vxo.h"
+#include "vxo_internal.h"
 #include <limits.h>
 #include <math.h>
 #include <stdio.h>
@@ -17,7 +18,7 @@
 
 /* ------------------------------------------------------------------------------------------ */
 /* constants: fshader.glsl:3-10, render.hpp:4-11                                               */
-#define RENDER_DIST 384
+#define RENDER_DIST VXO_RENDER_DIST
 #define LOCAL_LIGHT_DIST 64
 #define AMBIENT 0.4f
 #define DIFFUSE 0.8f
@@ -228,14 +229,14 @@ void vxo_remove_sphere(int32_t* vox, vxo_dims g, int px, int py, int pz, int rad
                         fix_depth_field_n(vox, g, x + px, y + py, z + pz, g_off_count);
 }
 
-static int f2i(float x);   /* below */
+static int vxo_f2i(float x);   /* below */
 
 /* controls.cpp:100-110 (the body under keys[RMB]); glm::ivec3(vec3) truncates */
 void vxo_do_destroy(int32_t* vox, vxo_dims g, const float cam_pos[3], const float cam_dir[3], float centre_out[3]) {
     float destroyRange = 15.0f;
     float c[3];
     for (int k = 0; k < 3; k++) c[k] = cam_pos[k] + destroyRange * cam_dir[k];
-    vxo_remove_sphere(vox, g, f2i(c[0]), f2i(c[1]), f2i(c[2]), (int)(destroyRange / 2));
+    vxo_remove_sphere(vox, g, vxo_f2i(c[0]), vxo_f2i(c[1]), vxo_f2i(c[2]), (int)(destroyRange / 2));
     if (centre_out) for (int k = 0; k < 3; k++) centre_out[k] = c[k];
 }
 
@@ -265,13 +266,6 @@ int vxo_partial_ranges(vxo_dims g, const float start_in[3], const float end_in[3
 /* ------------------------------------------------------------------------------------------ */
 /* shader: fshader.glsl                                                                        */
 
-/* float -> int: truncation; NaN / out of range -> INT_MIN (see vxo.h conventions) */
-static int f2i(float x) {
-    return (x >= -2147483648.0f && x < 2147483648.0f) ? (int)x : INT_MIN;
-}
-static float fsign(float x) { return (float)((0.0f < x) - (x < 0.0f)); }     /* GLM sign(): (0<x) - (x<0) */
-static float fmax0(float b) { return (0.0f < b) ? b : 0.0f; }                /* max(0, b) */
-
 /* fshader.glsl:33-52, generalised from (512,96,512) to (w,h,d).  The shader multiplies first and
  * range-checks the products; int arithmetic wraps. */
 int32_t vxo_shader_index(vxo_dims g, int32_t x, int32_t y, int32_t z) {
@@ -284,197 +278,20 @@ int32_t vxo_shader_index(vxo_dims g, int32_t x, int32_t y, int32_t z) {
     return hit;
 }
 
-/* the shader's mutable globals, fshader.glsl:28-31 */
-typedef struct {
-    float hitPos[3];
-    float hitNormal[3];
-    float stepCount;
-    uint64_t fetches;           /* instrumentation: iterations of every castRay call */
-} shader_state;
-
-/* ---- analysis only (scripts/where_iterations_go.py): where do castRay's iterations go? -------------------
- * Not part of the restatement: cast_ray() below fills the calling thread's profile when one is set and is
- * otherwise unchanged.  For every ray: its kind (set by the caller), how it ended, its iterations, how many of them
- * were depth-field jumps, and how many came AFTER the first moment at which its cell lay beyond every grid row that
- * holds a solid voxel in its direction of travel (tested at the start and after each jump, like the CUDA path's
- * occupancy-summary culling does). */
-static _Thread_local vxo_profile* tl_prof = NULL;
-static _Thread_local int tl_kind = 0, tl_dark = 0;
-static int tl_ymin = 0, tl_ymax = -1;          /* rows holding solids (set by vxo_profile_frame) */
-
-/* "clear box" experiment: castRay's cells only ever advance in the direction of travel and never run ahead of the ray's
- * position, and one iteration advances the ray parameter by at most 1/max|dir_i| per unit of budget, so every cell a
- * ray can visit lies in the axis-aligned box from its start cell to the cell of start + dir * (budget + 7) / max|dir_i|
- * (+ 2 cells of margin), cut at the rows that hold solids.  If a summed-area table says that box holds no solid voxel,
- * the ray is a miss without marching.  q = granularity of the table in x and z (the box is rounded outward to it). */
-static const uint32_t* sat = NULL;             /* (w+1)(h+1)(d+1) inclusive prefix counts of solid voxels */
-static vxo_dims sat_g;
-static uint64_t sat_at(int x, int y, int z) { return sat[((size_t)z * (sat_g.h + 1) + y) * (sat_g.w + 1) + x]; }
-static uint64_t sat_box(int x0, int x1, int y0, int y1, int z0, int z1) {   /* inclusive cell ranges */
-    return sat_at(x1 + 1, y1 + 1, z1 + 1) - sat_at(x0, y1 + 1, z1 + 1) - sat_at(x1 + 1, y0, z1 + 1) - sat_at(x1 + 1, y1 + 1, z0)
-         + sat_at(x0, y0, z1 + 1) + sat_at(x0, y1 + 1, z0) + sat_at(x1 + 1, y0, z0) - sat_at(x0, y0, z0);
-}
-static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-/* 1: none of the k boxes along the ray (start s, direction r, budget limit) holds a solid, table granularity q.
- * A cell castRay tests at ray parameter a (< T) is the cell that contains the point s + r*a (up to float fuzz far below
- * one cell), a < T = (limit + 1) / max|r_i| because before every iteration distTravelled < limit and n steps advance the
- * parameter by at most n / max|r_i|; box j covers the parameters [T*j/k, T*(j+1)/k] with one cell of margin in front and
- * behind, but never reaches behind the start cell (cells only advance in the direction of travel). */
-static int boxes_are_clear(float sx, float sy, float sz, float rx, float ry, float rz, float limit, int k, int q) {
-    const float ax = fabsf(rx), ay = fabsf(ry), az = fabsf(rz);
-    float rmax = ax > ay ? ax : ay; if (az > rmax) rmax = az;
-    if (!(rmax > 0.25f && rmax <= 2.0f) || !(fabsf(sx) < 1048576.0f && fabsf(sy) < 1048576.0f && fabsf(sz) < 1048576.0f)) return 0;
-    float T = (limit + 1.0f) / rmax;
-    /* rows beyond [ymin, ymax] hold nothing: the ray only matters until it has left them */
-    if (ry > 0.0f) { float te = ((float)(tl_ymax + 1) - sy) / ry; if (te < T) T = te; }
-    else if (ry < 0.0f) { float te = (sy - (float)tl_ymin) / -ry; if (te < T) T = te; }
-    if (!(T > 0.0f)) return 1;                                       /* already beyond every solid row */
-    const float s[3] = {sx, sy, sz}, r[3] = {rx, ry, rz};
-    const int ext[3] = {sat_g.w, sat_g.h, sat_g.d};
-    for (int j = 0; j < k; j++) {
-        const float t0 = T * (float)j / (float)k, t1 = T * (float)(j + 1) / (float)k;
-        int lo[3], hi[3], empty = 0;
-        for (int a = 0; a < 3; a++) {
-            const int c0 = (int)s[a];                                /* start cell: exact */
-            const int b0 = (int)floorf(s[a] + r[a] * t0), b1 = (int)floorf(s[a] + r[a] * t1);
-            if (r[a] >= 0.0f) { lo[a] = b0 - 1 > c0 ? b0 - 1 : c0; hi[a] = b1 + 1; }
-            else              { hi[a] = b0 + 1 < c0 ? b0 + 1 : c0; lo[a] = b1 - 1; }
-            if (a != 1 && q > 1) { lo[a] = (int)floorf((float)lo[a] / (float)q) * q; hi[a] = (int)floorf((float)hi[a] / (float)q) * q + q - 1; }
-            if (hi[a] < 0 || lo[a] > ext[a] - 1 || lo[a] > hi[a]) { empty = 1; break; }   /* outside the grid */
-            lo[a] = clampi(lo[a], 0, ext[a] - 1); hi[a] = clampi(hi[a], 0, ext[a] - 1);
-        }
-        if (empty) continue;
-        if (lo[1] < tl_ymin) lo[1] = tl_ymin;
-        if (hi[1] > tl_ymax) hi[1] = tl_ymax;
-        if (lo[1] > hi[1]) continue;
-        if (sat_box(lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]) != 0) return 0;
-    }
-    return 1;
-}
-static const int BOX_K[VXO_BOX_VARIANTS] = {1, 2, 4, 8, 16, 8, 8, 16};
-static const int BOX_Q[VXO_BOX_VARIANTS] = {1, 1, 1, 1, 1, 2, 4, 4};
-
-/* Check of the guards of ray.cuh's FAST_RUNS experiment (same integer / float operations).  Before a step of a shadow / light
- * ray that is not inside a run: if the wrapped index terms of the cell are at least FAST_RUN_MARGIN cells away from every
- * bound, a run of steps without range test begins; it ends when distTravelled reaches stop = min(limit, distTravelled0 +
- * (FAST_RUN_MARGIN - 1) - 0.5) or at the first voxel that is not empty.  Every step of a run is checked here to be in the
- * grid and to pass the reference's budget test, and no run to take more than FAST_RUN_MARGIN - 1 steps. */
-#define FAST_RUN_MARGIN 8
-typedef struct { int left, taken; float stop; } fast_run;
-static void fast_arm(fast_run* fr, vxo_dims g, int cx, int cy, int cz, float limit, float dist) {
-    const uint32_t W = (uint32_t)g.w, WH = W * (uint32_t)g.h, N = WH * (uint32_t)g.d, M = FAST_RUN_MARGIN;
-    const uint32_t px = (uint32_t)cx, py = (uint32_t)cy * W, pz = (uint32_t)cz * WH;
-    const uint32_t tx = g.w > 2 * FAST_RUN_MARGIN ? W - 2 * M : 0, ty = g.h > 2 * FAST_RUN_MARGIN ? WH - 2 * M * W : 0,
-                   tz = g.d > 2 * FAST_RUN_MARGIN ? N - 2 * M * WH : 0;
-    fr->left = (px - M < tx) && (py - M * W < ty) && (pz - M * WH < tz);
-    fr->taken = 0;
-    const float s2 = dist + ((float)(FAST_RUN_MARGIN - 1) - 0.5f);
-    fr->stop = limit < s2 ? limit : s2;
-}
-
-static void prof_ray(int outcome, uint64_t it, uint64_t jumps, uint64_t cull_it) {
-    vxo_profile* p = tl_prof;
-    if (!p) return;
-    vxo_profile_cell* c = &p->cell[tl_kind][outcome];
-    c->rays++; c->iterations += it; c->jumps += jumps;
-    if (cull_it < it) { c->rays_culled++; c->iterations_after_cull += it - cull_it; }
-    if (tl_dark) { c->rays_dark++; c->iterations_dark += it; if (cull_it < it) c->iterations_dark_after_cull += it - cull_it; }
-    if (it > p->longest[tl_kind]) p->longest[tl_kind] = it;
-}
-
-/* fshader.glsl:59-129 */
-static int32_t cast_ray(const int32_t* vox, vxo_dims g, shader_state* st,
-                        float sx, float sy, float sz, float rx, float ry, float rz, int32_t dist) {
-    int32_t cx = f2i(sx), cy = f2i(sy), cz = f2i(sz);               /* :64 */
-    int32_t fColorIndex = -1, tempIndex = -1;
-    int32_t stepx = f2i(fsign(rx)), stepy = f2i(fsign(ry)), stepz = f2i(fsign(rz));   /* :71 */
-    int32_t fwx = (stepx > 0), fwy = (stepy > 0), fwz = (stepz > 0);                  /* :72 */
-    float dx = 1.0f / fabsf(rx + 0.000001f);                        /* :74-76 */
-    float dy = 1.0f / fabsf(ry + 0.000001f);
-    float dz = 1.0f / fabsf(rz + 0.000001f);
-    /* :79  (ivec3 + ivec3 -> int add; converted to float; minus start; divided by direction) */
-    float ix = ((float)(int32_t)((uint32_t)cx + (uint32_t)fwx) - sx) / rx;
-    float iy = ((float)(int32_t)((uint32_t)cy + (uint32_t)fwy) - sy) / ry;
-    float iz = ((float)(int32_t)((uint32_t)cz + (uint32_t)fwz) - sz) / rz;
-    float currDist = 0.0f, distTravelled = 0.0f;
-    uint64_t p_it = 0, p_jumps = 0, p_cull = UINT64_MAX;            /* analysis only */
-    int p_outcome = 2;                                              /* 0 hit, 1 left the grid, 2 budget exhausted */
-    if (tl_prof && ((stepy > 0 && cy > tl_ymax) || (stepy < 0 && cy < tl_ymin))) p_cull = 0;
-    int p_clear[VXO_BOX_VARIANTS] = {0};
-    fast_run fr = {0, 0, 0.0f};
-    const float p_lim = (float)dist < (float)RENDER_DIST ? (float)dist : (float)RENDER_DIST;
-
-    if (tl_prof && sat && tl_kind != 0 && !tl_dark) {
-        const float lim = (float)dist < (float)RENDER_DIST ? (float)dist : (float)RENDER_DIST;
-        for (int v = 0; v < VXO_BOX_VARIANTS; v++) p_clear[v] = boxes_are_clear(sx, sy, sz, rx, ry, rz, lim, BOX_K[v], BOX_Q[v]);
-    }
-    while (distTravelled < (float)dist && distTravelled < (float)RENDER_DIST) {      /* :83 */
-        st->stepCount = st->stepCount + 1.0f;                       /* :84 */
-        st->fetches++;
-        p_it++;
-        if (tl_prof && tl_kind != 0 && fr.left == 0) {              /* analysis only: would an unchecked run begin here? */
-            fast_arm(&fr, g, cx, cy, cz, p_lim, distTravelled);
-            if (fr.left) tl_prof->fast_runs++;
-        }
-        distTravelled = distTravelled + 1.0f;                       /* :85 */
-        if (ix < iy && ix < iz) {                                   /* :87-92 */
-            currDist = ix; cx = (int32_t)((uint32_t)cx + (uint32_t)stepx); ix = ix + dx;
-            st->hitNormal[0] = (float)(-stepx); st->hitNormal[1] = 0.0f; st->hitNormal[2] = 0.0f;
-        } else if (iy < ix && iy < iz) {                            /* :93-98 */
-            currDist = iy; cy = (int32_t)((uint32_t)cy + (uint32_t)stepy); iy = iy + dy;
-            st->hitNormal[0] = 0.0f; st->hitNormal[1] = (float)(-stepy); st->hitNormal[2] = 0.0f;
-        } else {                                                    /* :99-104 (ties land here) */
-            currDist = iz; cz = (int32_t)((uint32_t)cz + (uint32_t)stepz); iz = iz + dz;
-            st->hitNormal[0] = 0.0f; st->hitNormal[1] = 0.0f; st->hitNormal[2] = (float)(-stepz);
-        }
-        tempIndex = vxo_shader_index(g, cx, cy, cz);                /* :105 */
-        if (tl_prof && fr.left > 0) {                               /* analysis only: a step of an unchecked run */
-            fr.taken++; tl_prof->fast_steps++;
-            if (tempIndex < 0 || fr.taken > FAST_RUN_MARGIN - 1) tl_prof->fast_guard_violations++;   /* left the grid / ran too long */
-            if (tempIndex >= 0 && vox[tempIndex] != -1) fr.left = 0;   /* event: the run ends here */
-            else if (!(distTravelled < fr.stop)) fr.left = 0;       /* the run is over: the checked block takes the next step ... */
-            else if (!(distTravelled < p_lim)) tl_prof->fast_guard_violations++;   /* ... and a step the reference would not take never starts */
-        }
-        if (tempIndex >= 0 && vox[tempIndex] >= 0) {                /* :108-112 */
-            st->hitPos[0] = rx * currDist + sx;
-            st->hitPos[1] = ry * currDist + sy;
-            st->hitPos[2] = rz * currDist + sz;
-            fColorIndex = tempIndex;
-            p_outcome = 0;
-            break;
-        } else if (tempIndex >= 0 && vox[tempIndex] != -1) {        /* :114-121 */
-            float bits; int32_t v = vox[tempIndex]; memcpy(&bits, &v, 4);
-            float toJump = -bits;
-            distTravelled = distTravelled + toJump;
-            currDist = currDist + toJump;
-            sx = rx * currDist + sx; sy = ry * currDist + sy; sz = rz * currDist + sz;
-            cx = f2i(sx); cy = f2i(sy); cz = f2i(sz);
-            ix = ((float)(int32_t)((uint32_t)cx + (uint32_t)fwx) - sx) / rx;
-            iy = ((float)(int32_t)((uint32_t)cy + (uint32_t)fwy) - sy) / ry;
-            iz = ((float)(int32_t)((uint32_t)cz + (uint32_t)fwz) - sz) / rz;
-            p_jumps++;
-            if (tl_prof && p_cull == UINT64_MAX && ((stepy > 0 && cy > tl_ymax) || (stepy < 0 && cy < tl_ymin))) p_cull = p_it;
-        } else if (tempIndex < 0) {                                 /* :123-125 */
-            p_outcome = 1;
-            break;
-        }
-    }
-    if (tl_prof) {
-        prof_ray(p_outcome, p_it, p_jumps, p_cull);
-        for (int v = 0; v < VXO_BOX_VARIANTS; v++)
-            if (p_clear[v]) {
-                vxo_profile_box* b = &tl_prof->box[tl_kind][v];
-                b->rays++;
-                b->iterations += (p_cull < p_it) ? p_cull : p_it;      /* what the CUDA path would still have marched */
-                if (p_outcome == 0) b->violations++;                   /* a clear tube and yet a hit: the ray left its line (tie lock) */
-            }
-    }
-    return fColorIndex;
-}
+/* fshader.glsl:59-129: the statement-for-statement loop lives in vxo_castray_body.inc, shared with the analysis translation
+ * units (oracle/vxo_analysis.c, oracle/vxo_trav.c), which define the VXO_HOOK_* macros; here they are empty, so this is
+ * the plain restatement and nothing else. */
+#define VXO_CAST_RAY_NAME cast_ray
+#define VXO_HOOK_ARGS
+#define VXO_HOOK_START()
+#define VXO_HOOK_ITER()
+#define VXO_HOOK_JUMP()
+#define VXO_HOOK_END(outcome)
+#include "vxo_castray_body.inc"
 
 int32_t vxo_cast_ray(const int32_t* vox, vxo_dims g, const float start[3], const float dir[3],
                      int32_t dist, vxo_ray_out* out) {
-    shader_state st; memset(&st, 0, sizeof st);
+    vxo_shader_state st; memset(&st, 0, sizeof st);
     int32_t r = cast_ray(vox, g, &st, start[0], start[1], start[2], dir[0], dir[1], dir[2], dist);
     if (out) {
         for (int k = 0; k < 3; k++) { out->hit_pos[k] = st.hitPos[k]; out->hit_normal[k] = st.hitNormal[k]; }
@@ -494,12 +311,20 @@ static void normalize3(const float v[3], float out[3]) {
     out[0] = v[0] * inv; out[1] = v[1] * inv; out[2] = v[2] * inv;
 }
 
-/* fshader.glsl:131-190 */
-void vxo_shade_pixel(const int32_t* vox, vxo_dims g, const vxo_frame* f, int width, int height,
-                     int px, int py, float rgba[4], int32_t* hit_index, float* steps,
-                     uint32_t* occl_mask, uint32_t* cast_mask, float hit_pos[3], float hit_normal[3],
-                     uint64_t counters[5]) {
-    shader_state st; memset(&st, 0, sizeof st);
+/* fshader.glsl:131-190.  `castRay` is the castRay to use: cast_ray above for the oracle proper; the analysis translation units
+ * pass their instrumented / traversal-grid variants (ray kind: 0 primary, 1 global light, 2 local light; dark: the surface
+ * faces away from the light -- both ignored by the plain cast_ray). */
+static int32_t cast_ray_plain(void* user, const int32_t* vox, vxo_dims g, vxo_shader_state* st, float sx, float sy, float sz,
+                              float rx, float ry, float rz, int32_t dist, int kind, int dark) {
+    (void)user; (void)kind; (void)dark;
+    return cast_ray(vox, g, st, sx, sy, sz, rx, ry, rz, dist);
+}
+
+void vxo_shade_pixel_with(vxo_cast_fn castRay, void* user, const int32_t* vox, vxo_dims g, const vxo_frame* f, int width, int height,
+                          int px, int py, float rgba[4], int32_t* hit_index, float* steps,
+                          uint32_t* occl_mask, uint32_t* cast_mask, float hit_pos[3], float hit_normal[3],
+                          uint64_t counters[5]) {
+    vxo_shader_state st; memset(&st, 0, sizeof st);
     /* vshader.glsl:6-9 + quad render.cpp:36-44: vPos = NDC of the pixel centre */
     float vx = ((float)px + 0.5f) / (float)width * 2.0f - 1.0f;
     float vy = ((float)py + 0.5f) / (float)height * 2.0f - 1.0f;
@@ -513,8 +338,7 @@ void vxo_shade_pixel(const int32_t* vox, vxo_dims g, const vxo_frame* f, int wid
         float mul0 = m[0 + r] * rd[0], mul1 = m[4 + r] * rd[1], mul2 = m[8 + r] * rd[2], mul3 = m[12 + r] * 0.0f;
         rot[r] = (mul0 + mul1) + (mul2 + mul3);
     }
-    tl_kind = 0; tl_dark = 0;
-    int32_t idx = cast_ray(vox, g, &st, f->cam_pos[0], f->cam_pos[1], f->cam_pos[2], rot[0], rot[1], rot[2], RENDER_DIST);   /* :139 */
+    int32_t idx = castRay(user, vox, g, &st, f->cam_pos[0], f->cam_pos[1], f->cam_pos[2], rot[0], rot[1], rot[2], RENDER_DIST, 0, 0);   /* :139 */
     float fhp[3] = {st.hitPos[0], st.hitPos[1], st.hitPos[2]};      /* :140 */
     float fhn[3] = {st.hitNormal[0], st.hitNormal[1], st.hitNormal[2]};   /* :141 */
     float primary_steps = st.stepCount;
@@ -531,10 +355,9 @@ void vxo_shade_pixel(const int32_t* vox, vxo_dims g, const vxo_frame* f, int wid
         if (idx != -1 && vox[idx] >= 0) {                           /* :152 */
             hit = 1;
             cast |= 1u; n_global++;
-            tl_kind = 1; tl_dark = !(0.0f < dot3(fhn, toLight));    /* analysis only */
-            if (cast_ray(vox, g, &st, fhp[0] + toLight[0] * 0.001f, fhp[1] + toLight[1] * 0.001f, fhp[2] + toLight[2] * 0.001f,
-                         toLight[0], toLight[1], toLight[2], RENDER_DIST) == -1) {            /* :154 */
-                multiplier = multiplier + DIFFUSE * fmax0(dot3(fhn, toLight));                /* :155 */
+            if (castRay(user, vox, g, &st, fhp[0] + toLight[0] * 0.001f, fhp[1] + toLight[1] * 0.001f, fhp[2] + toLight[2] * 0.001f,
+                     toLight[0], toLight[1], toLight[2], RENDER_DIST, 1, !(0.0f < dot3(fhn, toLight))) == -1) {   /* :154 */
+                multiplier = multiplier + DIFFUSE * vxo_fmax0(dot3(fhn, toLight));                /* :155 */
             } else occl |= 1u;
             for (int i = 0; i < VXO_MAX_LOCAL_LIGHTS; i++) {        /* :159 */
                 if (multiplier >= MAX_OVERBRIGHT) { multiplier = MAX_OVERBRIGHT; break; }     /* :161-164 */
@@ -544,10 +367,9 @@ void vxo_shade_pixel(const int32_t* vox, vxo_dims g, const vxo_frame* f, int wid
                     if (lld <= (float)LOCAL_LIGHT_DIST) {           /* :171 */
                         float tll[3]; normalize3(d, tll);           /* :173 */
                         cast |= 2u << i; n_local++;
-                        tl_kind = 2; tl_dark = !(0.0f < dot3(fhn, tll));   /* analysis only */
-                        if (cast_ray(vox, g, &st, fhp[0] + tll[0] * 0.001f, fhp[1] + tll[1] * 0.001f, fhp[2] + tll[2] * 0.001f,
-                                     tll[0], tll[1], tll[2], f2i(lld + 1.0f)) == -1) {        /* :175 */
-                            multiplier = multiplier + f->lights[i][3] * fmax0(dot3(fhn, tll)) *
+                        if (castRay(user, vox, g, &st, fhp[0] + tll[0] * 0.001f, fhp[1] + tll[1] * 0.001f, fhp[2] + tll[2] * 0.001f,
+                                 tll[0], tll[1], tll[2], vxo_f2i(lld + 1.0f), 2, !(0.0f < dot3(fhn, tll))) == -1) {   /* :175 */
+                            multiplier = multiplier + f->lights[i][3] * vxo_fmax0(dot3(fhn, tll)) *
                                          (((float)LOCAL_LIGHT_DIST - lld) / (float)LOCAL_LIGHT_DIST);   /* :177 */
                         } else occl |= 2u << i;
                     }
@@ -570,6 +392,14 @@ void vxo_shade_pixel(const int32_t* vox, vxo_dims g, const vxo_frame* f, int wid
     if (counters) {
         counters[0] += 1; counters[1] += n_global; counters[2] += n_local; counters[3] += st.fetches; counters[4] += (uint64_t)hit;
     }
+}
+
+void vxo_shade_pixel(const int32_t* vox, vxo_dims g, const vxo_frame* f, int width, int height,
+                     int px, int py, float rgba[4], int32_t* hit_index, float* steps,
+                     uint32_t* occl_mask, uint32_t* cast_mask, float hit_pos[3], float hit_normal[3],
+                     uint64_t counters[5]) {
+    vxo_shade_pixel_with(cast_ray_plain, NULL, vox, g, f, width, height, px, py, rgba, hit_index, steps, occl_mask, cast_mask,
+                         hit_pos, hit_normal, counters);
 }
 
 /* default-framebuffer store: RGBA8 UNORM */
@@ -613,67 +443,3 @@ void vxo_render(const int32_t* vox, vxo_dims g, const vxo_frame* f, int width, i
     if (counters) for (int k = 0; k < 5; k++) counters[k] += tot[k];
 }
 
-/* analysis only: vxo_render's loop with the per-ray profile switched on; out is accumulated over all threads */
-void vxo_profile_frame(const int32_t* vox, vxo_dims g, const vxo_frame* f, int width, int height, vxo_profile* out) {
-    int ymin = INT_MAX, ymax = INT_MIN;
-    for (int z = 0; z < g.d; z++)
-        for (int y = 0; y < g.h; y++) {
-            if (y >= ymin && y <= ymax) continue;
-            const int32_t* row = vox + ((size_t)z * g.h + y) * g.w;
-            for (int x = 0; x < g.w; x++) if (row[x] >= 0) { if (y < ymin) ymin = y; if (y > ymax) ymax = y; break; }
-        }
-    tl_ymin = ymin; tl_ymax = ymax;
-    {   /* inclusive 3-D prefix counts of solid voxels */
-        const size_t W1 = (size_t)g.w + 1, H1 = (size_t)g.h + 1, D1 = (size_t)g.d + 1;
-        uint32_t* t = (uint32_t*)calloc(W1 * H1 * D1, sizeof(uint32_t));
-        for (size_t z = 1; z < D1; z++)
-            for (size_t y = 1; y < H1; y++) {
-                uint32_t run = 0;
-                const int32_t* row = vox + ((z - 1) * g.h + (y - 1)) * g.w;
-                for (size_t x = 1; x < W1; x++) {
-                    run += row[x - 1] >= 0;
-                    t[(z * H1 + y) * W1 + x] = run + t[(z * H1 + y - 1) * W1 + x] + t[((z - 1) * H1 + y) * W1 + x] - t[((z - 1) * H1 + y - 1) * W1 + x];
-                }
-            }
-        sat = t; sat_g = g;
-    }
-    memset(out, 0, sizeof *out);
-    out->ymin = ymin; out->ymax = ymax;
-#ifdef _OPENMP
-#pragma omp parallel
-#endif
-    {
-        vxo_profile loc; memset(&loc, 0, sizeof loc);
-        tl_prof = &loc;
-#ifdef _OPENMP
-#pragma omp for schedule(dynamic, 4)
-#endif
-        for (int py = 0; py < height; py++)
-            for (int px = 0; px < width; px++) {
-                float rgba[4];
-                vxo_shade_pixel(vox, g, f, width, height, px, py, rgba, NULL, NULL, NULL, NULL, NULL, NULL, NULL);
-            }
-        tl_prof = NULL;
-#ifdef _OPENMP
-#pragma omp critical
-#endif
-        {
-            for (int k = 0; k < 3; k++) {
-                for (int o = 0; o < 3; o++) {
-                    vxo_profile_cell* a = &out->cell[k][o]; const vxo_profile_cell* b = &loc.cell[k][o];
-                    a->rays += b->rays; a->iterations += b->iterations; a->jumps += b->jumps; a->rays_culled += b->rays_culled;
-                    a->iterations_after_cull += b->iterations_after_cull; a->rays_dark += b->rays_dark;
-                    a->iterations_dark += b->iterations_dark; a->iterations_dark_after_cull += b->iterations_dark_after_cull;
-                }
-                if (loc.longest[k] > out->longest[k]) out->longest[k] = loc.longest[k];
-                if (k == 0) { out->fast_runs += loc.fast_runs; out->fast_steps += loc.fast_steps; out->fast_guard_violations += loc.fast_guard_violations; }
-                for (int v = 0; v < VXO_BOX_VARIANTS; v++) {
-                    out->box[k][v].rays += loc.box[k][v].rays; out->box[k][v].iterations += loc.box[k][v].iterations;
-                    out->box[k][v].violations += loc.box[k][v].violations;
-                }
-            }
-        }
-    }
-    free((void*)sat);
-    sat = NULL;
-}

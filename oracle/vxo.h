@@ -113,7 +113,7 @@ void vxo_shade_pixel(const int32_t* vox, vxo_dims g, const vxo_frame* f, int wid
 
 int vxo_num_threads(void);
 
-/* ---- analysis only (scripts/where_iterations_go.py; not part of the restatement) ----------------------------
+/* ---- analysis only (oracle/vxo_analysis.c, scripts/where_iterations_go.py; not part of the restatement) ----------
  * cell[kind][outcome]: kind 0 primary / 1 global-light / 2 local-light ray; outcome 0 hit / 1 left the grid /
  * 2 budget exhausted.  "after_cull": iterations that came after the ray's cell first lay beyond every grid row holding
  * a solid, in its direction of travel (the CUDA path's occupancy-summary culling ends the ray there).  "dark": rays
@@ -123,16 +123,24 @@ typedef struct {
     uint64_t rays_culled, iterations_after_cull;
     uint64_t rays_dark, iterations_dark, iterations_dark_after_cull;
 } vxo_profile_cell;
-#define VXO_BOX_VARIANTS 8           /* clear-box test: (boxes along the ray, x/z granularity of the table), see vxo.c */
-typedef struct { uint64_t rays, iterations, violations; } vxo_profile_box;   /* lit shadow / light rays whose box is clear */
 typedef struct {
     vxo_profile_cell cell[3][3];
-    vxo_profile_box box[3][VXO_BOX_VARIANTS];
     uint64_t longest[3];            /* most iterations of a single ray, per kind */
-    uint64_t fast_runs, fast_steps, fast_guard_violations;   /* ray.cuh FAST_RUNS: unchecked runs, their steps, failed guards (must be 0) */
     int32_t ymin, ymax;             /* rows that hold a solid voxel */
 } vxo_profile;
 void vxo_profile_frame(const int32_t* vox, vxo_dims g, const vxo_frame* f, int width, int height, vxo_profile* out);
+
+
+/* ---- traversal grid of the CUDA path, restated on the host (oracle/vxo_trav.c; not part of the reference) ------------
+ * word of one cell / of the whole grid (returns the number of values that cannot be encoded), the reference value of a
+ * word, castRay and vxo_render on a traversal grid (stats9: fast steps, checked steps, jumps per ray kind 0/1/2). */
+int32_t vxo_trav_word(const int32_t* vox, vxo_dims g, int x, int y, int z);
+int64_t vxo_trav_build(const int32_t* vox, vxo_dims g, int32_t* trav);
+int32_t vxo_trav_canonical(int32_t w);
+int32_t vxo_trav_cast_ray(const int32_t* trav, vxo_dims g, const float start[3], const float dir[3], int32_t dist, vxo_ray_out* out);
+void vxo_trav_render(const int32_t* trav, vxo_dims g, const vxo_frame* f, int width, int height, int y0, int y1,
+                     uint8_t* rgba8, int32_t* hit_index, uint16_t* steps, uint32_t* occl_mask, uint32_t* cast_mask,
+                     uint64_t counters[5], uint64_t stats9[9]);
 
 #ifdef __cplusplus
 }

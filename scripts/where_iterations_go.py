@@ -3,10 +3,11 @@ NO occupancy structure ever save?  Every ray of a frame is classified by kind (p
 by how it ended (hit / left the grid / budget exhausted).  A ray that hits must run every iteration (the first-hit voxel
 and hitPos depend on the whole float state), so only the iterations of rays that end as misses are avoidable at all;
 of those the table shows what the CUDA path already removes (occupancy-summary culling, unlit rays) and what is left for
-any finer brick hierarchy.  Two experiments ride along: the "clear tube" test (summed-area table of solid voxels: is the
-tube between a surface point and its light empty?) with the number of rays that HIT although their tube is clear (tie locks),
-and a replay of the guards of ray.cuh's FAST_RUNS experiment on every shadow / light ray.  Usage: python scripts/where_iterations_go.py [--size 3840 2160] [--case C3ii C3ii_pitched]
-Writes profiles/r1_where_iterations_go.json with --write."""
+any finer brick hierarchy; and, with the traversal grid of the CUDA path restated on the host (oracle/vxo_trav.c), how many
+iterations become steps of a run that needs no index arithmetic, range test or load.  (Round 1's "clear tube" experiment --
+a summed-area table of solids; inexact because of the reference's tie locks -- is recorded in profiles/r1_where_iterations_go.json.)
+Usage: python scripts/where_iterations_go.py [--size 3840 2160] [--case C2 C3ii_pitched]
+Writes profiles/r2_where_iterations_go.json with --write."""
 import argparse
 import ctypes as C
 import json
@@ -27,15 +28,8 @@ class Cell(C.Structure):
                                           "rays_dark", "iterations_dark", "iterations_dark_after_cull")]
 
 
-class Box(C.Structure):
-    _fields_ = [("rays", C.c_uint64), ("iterations", C.c_uint64), ("violations", C.c_uint64)]
-
-
-BOX_KQ = ((1, 1), (2, 1), (4, 1), (8, 1), (16, 1), (8, 2), (8, 4), (16, 4))
-
-
 class Profile(C.Structure):
-    _fields_ = [("cell", (Cell * 3) * 3), ("box", (Box * 8) * 3), ("longest", C.c_uint64 * 3), ("fast_runs", C.c_uint64), ("fast_steps", C.c_uint64), ("fast_guard_violations", C.c_uint64), ("ymin", C.c_int32), ("ymax", C.c_int32)]
+    _fields_ = [("cell", (Cell * 3) * 3), ("longest", C.c_uint64 * 3), ("ymin", C.c_int32), ("ymax", C.c_int32)]
 
 
 KINDS = ("primary", "global_light", "local_light")
@@ -46,11 +40,7 @@ def profile(o, level, dims, frame, w, h):
     p = Profile()
     o.L.vxo_profile_frame.restype = None
     o.L.vxo_profile_frame(level.ctypes.data_as(C.POINTER(C.c_int32)), ol.Dims(*dims), C.byref(frame), C.c_int(w), C.c_int(h), C.byref(p))
-    out = {"fast_runs": {"runs": int(p.fast_runs), "steps": int(p.fast_steps), "guard_violations": int(p.fast_guard_violations)},
-           "ymin": p.ymin, "ymax": p.ymax, "longest": {k: int(p.longest[i]) for i, k in enumerate(KINDS)}, "cells": {},
-           "clear_box": {"%s/k%d_q%d" % (k, kq[0], kq[1]): {"rays": int(p.box[i][v].rays), "iterations_saved": int(p.box[i][v].iterations),
-                                             "violations": int(p.box[i][v].violations)}
-                         for i, k in enumerate(KINDS) if i for v, kq in enumerate(BOX_KQ)}}
+    out = {"ymin": p.ymin, "ymax": p.ymax, "longest": {k: int(p.longest[i]) for i, k in enumerate(KINDS)}, "cells": {}}
     for i, k in enumerate(KINDS):
         for j, oc in enumerate(OUTCOMES):
             c = p.cell[i][j]
@@ -101,14 +91,18 @@ def main():
                     k, c["rays"], c["iterations"], c["iterations"] / c["rays"], 100.0 * c["jumps"] / max(1, c["iterations"]),
                     c["iterations_after_cull"], c["iterations_dark"]))
         print("  " + json.dumps(s))
-        shadow_it = sum(c["iterations"] for k, c in pr["cells"].items() if not k.startswith("primary/"))
-        print("  FAST_RUNS experiment (ray.cuh): %d unchecked runs cover %d of the %d iterations of shadow / light rays (%.1f%%), guard violations %d" % (
-            pr["fast_runs"]["runs"], pr["fast_runs"]["steps"], shadow_it, 100.0 * pr["fast_runs"]["steps"] / max(1, shadow_it), pr["fast_runs"]["guard_violations"]))
-        for k, b in pr["clear_box"].items():
-            print("  clear box %-24s rays %10d  iterations saved %11d (%.1f%% of those still executed)  violations %d" % (
-                k, b["rays"], b["iterations_saved"], 100.0 * b["iterations_saved"] / s["still_executed"], b["violations"]))
+        # the traversal grid of the CUDA path (oracle/vxo_trav.c): how many of the iterations become steps of a run (no index
+        # arithmetic, range test or load) -- counted on every ray the reference casts, per ray kind
+        trav, bad = o.trav_build(level, gc.DIMS)
+        tr = o.trav_render(trav, gc.DIMS, fr, w, h)
+        st = [int(v) for v in tr["stats"]]
+        pr["traversal_grid"] = {k: {"run_steps": st[i], "checked_steps": st[3 + i], "of_which_jumps": st[6 + i]} for i, k in enumerate(KINDS)}
+        pr["traversal_grid"]["unencodable_values"] = bad
+        for i, k in enumerate(KINDS):
+            print("  traversal grid %-14s run steps %11d  checked steps %11d (jumps %10d)  -> %.1f%% of the iterations need no load" % (
+                k, st[i], st[3 + i], st[6 + i], 100.0 * st[i] / max(1, st[i] + st[3 + i])))
     if a.write:
-        path = os.path.join(ROOT, "profiles", "r1_where_iterations_go.json")
+        path = os.path.join(ROOT, "profiles", "r2_where_iterations_go.json")
         with open(path, "w") as f:
             json.dump(result, f, indent=1)
         print("wrote", path)

@@ -157,6 +157,41 @@ class Oracle:
     def num_threads(self):
         return int(self.L.vxo_num_threads())
 
+    # ---- host statement of the CUDA path's traversal grid (oracle/vxo_trav.c) ----
+    def trav_build(self, vox, dims):
+        """(traversal grid, number of values that cannot be encoded)"""
+        trav = np.empty(vox.size, np.int32)
+        self.L.vxo_trav_build.restype = C.c_int64
+        bad = self.L.vxo_trav_build(_ptr(np.ascontiguousarray(vox), C.c_int32), Dims(*dims), _ptr(trav, C.c_int32))
+        return trav, int(bad)
+
+    @staticmethod
+    def trav_canonical(trav):
+        """reference values of traversal words: band words (negative, bit 30 clear) -> -1"""
+        t = np.asarray(trav, np.int32)
+        return np.where((t < 0) & ((t & 0x40000000) == 0), np.int32(-1), t)
+
+    def trav_cast_ray(self, trav, dims, start, direction, dist):
+        out = RayOut()
+        s = (C.c_float * 3)(*[float(v) for v in start])
+        d = (C.c_float * 3)(*[float(v) for v in direction])
+        self.L.vxo_trav_cast_ray.restype = C.c_int32
+        r = self.L.vxo_trav_cast_ray(_ptr(trav, C.c_int32), Dims(*dims), s, d, C.c_int32(int(dist)), C.byref(out))
+        return r, np.array(out.hit_pos, np.float32), np.array(out.hit_normal, np.float32), float(out.steps)
+
+    def trav_render(self, trav, dims, frame, width, height, y0=0, y1=None):
+        """vxo_render on a traversal grid; also 'stats': fast steps / checked steps / jumps per ray kind"""
+        y1 = height if y1 is None else y1
+        out = dict(rgba8=np.zeros((height, width, 4), np.uint8), hit_index=np.full((height, width), -2, np.int32),
+                   steps=np.zeros((height, width), np.uint16), occl_mask=np.zeros((height, width), np.uint32),
+                   cast_mask=np.zeros((height, width), np.uint32), counters=np.zeros(5, np.uint64), stats=np.zeros(9, np.uint64))
+        self.L.vxo_trav_render.restype = None
+        self.L.vxo_trav_render(_ptr(trav, C.c_int32), Dims(*dims), C.byref(frame), C.c_int(width), C.c_int(height),
+                               C.c_int(y0), C.c_int(y1), _ptr(out["rgba8"], C.c_uint8), _ptr(out["hit_index"], C.c_int32),
+                               _ptr(out["steps"], C.c_uint16), _ptr(out["occl_mask"], C.c_uint32), _ptr(out["cast_mask"], C.c_uint32),
+                               _ptr(out["counters"], C.c_uint64), _ptr(out["stats"], C.c_uint64))
+        return out
+
 
 def ref_available():
     return all(os.path.exists(os.path.join(REF_DIR, f)) for f in ("libref_host.so", "libref_shader.so"))

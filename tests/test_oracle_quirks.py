@@ -60,32 +60,3 @@ def test_iteration_profile_accounts_for_every_ray(oracle, default_level):
     assert (pr["ymin"], pr["ymax"]) == (0, 51)
     s = wig.summarise(pr)
     assert s["removed_total"] + s["still_executed"] == s["iterations"] and 0 < s["still_executed_by_misses"] < s["still_executed"]
-    # a lit local-light ray whose tube of boxes holds no solid voxel must reach its light -- unless a tie lock takes it off
-    # its line: one such ray in this small frame already, which is what rules the test out as an exact culling rule
-    box = pr["clear_box"]["local_light/k8_q1"]
-    assert box["rays"] > 50000 and box["violations"] == 1
-    assert all(b["violations"] == 0 for k, b in pr["clear_box"].items() if k.startswith("global_light/"))
-    # guards of ray.cuh's FAST_RUNS experiment: every step of every unchecked run is in the grid and within the budget
-    shadow_it = sum(c["iterations"] for k, c in pr["cells"].items() if not k.startswith("primary/"))
-    assert pr["fast_runs"]["guard_violations"] == 0 and 0.9 * shadow_it < pr["fast_runs"]["steps"] <= shadow_it
-
-
-def test_fast_run_guards_next_to_the_faces(oracle):
-    """the same guards on a grid whose cells are all close to a face, and on one smaller than twice the margin"""
-    sys.path.insert(0, os.path.join(ROOT, "scripts"))
-    import where_iterations_go as wig
-    rs = np.random.RandomState(3)
-    for dims, expect_runs in (((40, 24, 40), True), ((15, 15, 15), False)):
-        level = np.full(dims[0] * dims[1] * dims[2], -1, np.int32)
-        gv = level.reshape(dims[2], dims[1], dims[0])
-        gv[:, :5, :] = 0x406040
-        for _ in range(10):
-            x, y, z = rs.randint(2, dims[0] - 2), rs.randint(5, dims[1] - 4), rs.randint(2, dims[2] - 2)
-            gv[z - 1:z + 2, 5:y, x - 1:x + 2] = int(rs.randint(0, 1 << 24))
-        oracle.compute_depth_field(level, dims)
-        cam = (dims[0] / 2.0, dims[1] * 0.6, 1.5)
-        fr = ol.make_frame(cam, aspect=np.float32(16) / np.float32(9), light_pos=(dims[0] / 2.0, dims[1] * 5.0, dims[2] / 2.0),
-                           lights=[(2.0 + (dims[0] - 4) * i / 5.0, 7.0, 3.0 + (dims[2] - 6) * i / 5.0, 0.5) for i in range(6)])
-        pr = wig.profile(oracle, level, dims, fr, 192, 108)
-        assert pr["fast_runs"]["guard_violations"] == 0
-        assert (pr["fast_runs"]["runs"] > 0) == expect_runs
