@@ -690,6 +690,7 @@ def experiments(workload, production_fnv):
         except Exception as e:
             return {"error": repr(e)[:300]}
     out["production"] = run("production", {})
+    out["without_traversal_grid"] = run("without_traversal_grid", {"VXRT_TRAVERSAL": "0"})     # the plain kernels on the reference-layout grid
     import voxel_rt_b200 as vx
     for name in sorted(vx.build.VARIANTS):                         # variant libraries (voxel_rt_b200.build.VARIANTS), built here
         lib = None

@@ -121,6 +121,10 @@ int vxrt_load_grid(vxrt_ctx* ctx, const char* path);
 /* placeVoxel render.cpp:256-262 / destroyVoxel render.cpp:265-271 applied to the device grid */
 int vxrt_place_voxel(vxrt_ctx* ctx, int x, int y, int z, int32_t voxel);
 int vxrt_destroy_voxel(vxrt_ctx* ctx, int x, int y, int z);
+/* n placeVoxel calls as ONE staged copy + one kernel (the reference places voxels in bulk: placeBush level.cpp:21, placeTrunk
+   level.cpp:74, initVoxels level.cpp:102,113,124); xyz = n * 3 ints, voxels = n values; cells outside the grid are ignored,
+   where cells repeat the last entry wins -- exactly what the sequence of calls would leave */
+int vxrt_place_voxels(vxrt_ctx* ctx, size_t n, const int32_t* xyz, const int32_t* voxels);
 /* removeSphere(pos, radius) level.cpp:30-56 executed on the device grid (carve + fixDepthField over the
    radius+3 sphere); no host upload needed afterwards */
 int vxrt_edit_remove_sphere(vxrt_ctx* ctx, int cx, int cy, int cz, int radius);
@@ -163,6 +167,17 @@ int vxrt_set_l2_prefetch(vxrt_ctx* ctx, int mode);
    (their term is multiplied by max(0, N.L) = 0).  The first-hit voxel and every pixel are unchanged (ray.cuh CULL,
    kernels.cuh skip_dark); ray statistics always count the rays the reference casts. */
 int vxrt_set_culling(vxrt_ctx* ctx, int enabled);
+/* The TRAVERSAL GRID (csrc/trav.cuh; north_star item 1): the device copy of the grid the rays read.  Same index and 4 bytes per
+   cell as the reference layout; a -1 cell (empty, no depth-field jump) carries, per travel quadrant, how many further cells of
+   its y layer (and of the layer above) are -1 cells inside the grid, and castRay takes those steps without index arithmetic,
+   range test or load -- exact by adjacency: a step moves one cell along one axis whatever the float state says.  It is kept
+   coherent by every upload / edit entry point (a rebuild over the cells whose words can change).  enabled (default): rays read
+   it; disabled: rays read the reference-layout grid with the plain kernels.  Same pixels either way.  vxrt_traversal_active:
+   1 if the next frame reads the traversal grid (0 also when the grid holds a value that cannot be encoded: a negative int
+   with bit 30 clear other than through -1, which the reference never produces).  vxrt_download_traversal: the words, for tests. */
+int vxrt_set_traversal(vxrt_ctx* ctx, int enabled);
+int vxrt_traversal_active(vxrt_ctx* ctx);
+int vxrt_download_traversal(vxrt_ctx* ctx, int32_t* out, size_t count);
 /* enabled (default): the primary pass records how long each tile's block took and the next frame launches the
    slowest tiles first (shorter kernel tail; it matters when a GPU renders only a fraction of the frame).  Same pixels. */
 int vxrt_set_tile_ordering(vxrt_ctx* ctx, int enabled);

@@ -1,6 +1,6 @@
 """One kernel experiment, timed and checked in a process of its own (bench.py's "experiments" object; also usable by hand).
-The environment selects the build: nothing (the production library), VXRT_FAST_RUNS=1 (ray.cuh FAST_RUNS), or
-VXRT_LIB=<variant library>.  Renders the benchmark workload like bench.py's timed loop (production kernel variants, L2 flushed
+The environment selects the build: nothing (the production library), VXRT_TRAVERSAL=0 (the plain kernels on the reference-layout
+grid instead of the traversal grid), or VXRT_LIB=<variant library>.  Renders the benchmark workload like bench.py's timed loop (production kernel variants, L2 flushed
 between frames, CUDA events inside vxrt_render) and prints ONE JSON line: per-kernel and per-frame milliseconds and the
 FNV-1a-64 of the RGBA8 frame, which the caller compares with the production frame (bit-exactness).
     python scripts/exp_probe.py [--workload C3ii_4k] [--frames 40]"""
@@ -61,7 +61,7 @@ try:
     share = {"ms_primary": round(statistics.mean(p8), 4), "ms_shade": round(statistics.mean(s8), 4), "ms_per_frame": round(statistics.mean(t8), 4)}
 except Exception as e:               # the full-frame figures above must survive
     share = {"error": repr(e)[:200]}
-out = {"lib": os.path.basename(vx.build.lib_path()), "fast_runs": os.environ.get("VXRT_FAST_RUNS") == "1", "workload": a.workload,
+out = {"lib": os.path.basename(vx.build.lib_path()), "traversal": os.environ.get("VXRT_TRAVERSAL", "1") != "0", "workload": a.workload,
        "frames": a.frames, "ms_primary": round(statistics.mean(p), 4), "ms_shade": round(statistics.mean(s), 4),
        "ms_per_frame": round(statistics.mean(t), 4), "ms_per_frame_min": round(min(t), 4),
        "one_of_8_ranks": share,

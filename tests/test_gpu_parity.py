@@ -697,62 +697,126 @@ def test_local_light_slots(vx):
         assert r.getFrame().aspect == 4.0                                          # reshape, render.cpp:410
 
 
-# ---- experiments (off by default in the library; their tests are gated until they have run on a B200 once) ------------
-def test_fast_runs_experiment_in_a_subprocess():
-    """ray.cuh FAST_RUNS (off by default), in a process of its own; bit-exact on the B200 in round 1's final run"""
-    out = run_variant_check("FAST_RUNS", VXRT_FAST_RUNS="1")
-    assert "FAST_RUNS ok" in out
+# ---- the traversal grid (csrc/trav.cuh): the device copy the rays read ------------------------------------------------------
+def check_traversal_grid(oracle, r, dims, what):
+    """the device's traversal words == a host rebuild (oracle/vxo_trav.c) from the device's own reference-layout grid"""
+    level = r.downloadGrid()
+    want, bad = oracle.trav_build(level, dims)
+    got = r.downloadTraversal()
+    nbad = int((got != want).sum())
+    assert nbad == 0, "%s: %d traversal words differ from the host rebuild" % (what, nbad)
+    assert r.traversalActive() == (bad == 0), what
+    return level
 
 
-def run_variant_check(label, **env):
-    import subprocess
-    import sys
-    here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, os.path.join(here, "variant_check.py"), label], env=dict(os.environ, **env),
-                       capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
-    return r.stdout
+def test_traversal_grid_is_kept_coherent_by_every_entry_point(vx, oracle, golden, default_level, tmp_path):
+    dims = gc.DIMS
+    with vx.Renderer(grid=dims, width=32, height=8) as r:
+        r.updateGeometry(default_level)                                          # full upload
+        check_traversal_grid(oracle, r, dims, "upload")
+        host = default_level.copy()
+        for dd in golden["ref_host"]["destroys"]:                                # the reference's destroy sequence (device edits)
+            r.doDestroy(dd["cam"], dd["dir"])
+        lvl = check_traversal_grid(oracle, r, dims, "destroy sequence")
+        assert h64(oracle, lvl) == golden["ref_host"]["destroys"][-1]["fnv"]
+        rs = np.random.RandomState(17)
+        for _ in range(6):                                                       # craters incl. next to / across the faces
+            c = (int(rs.randint(-3, 515)), int(rs.randint(28, 50)), int(rs.randint(-3, 515)))
+            r.removeSphere(c, int(rs.randint(1, 9)))
+        check_traversal_grid(oracle, r, dims, "random craters")
+        r.placeVoxel(200, 37, 200, 0x123456); r.placeVoxel(201, 38, 200, 0x123456); r.destroyVoxel(100, 36, 100)
+        r.placeVoxel(0, 37, 0, 0x10); r.placeVoxel(511, 38, 511, 0x10)
+        check_traversal_grid(oracle, r, dims, "single voxels")
+        pts = np.stack([rs.randint(150, 260, 400), rs.randint(36, 42, 400), rs.randint(150, 260, 400)], 1)
+        vals = rs.randint(0, 1 << 24, 400).astype(np.int32)
+        vals[::7] = -1
+        pts[5] = pts[3]; pts[9] = (-4, 40, 10)                                   # a repeated cell (last wins), a cell outside the grid
+        r.placeVoxels(pts, vals)
+        lvl2 = check_traversal_grid(oracle, r, dims, "voxel batch")
+        want = lvl.copy()
+
+        def idx(x, y, z):
+            return x + 512 * y + 512 * 96 * z
+        for (x, y, z), v in zip(pts, vals):                                      # the batch replayed in order on the host (its cells only)
+            if 0 <= x < 512 and 0 <= y < 96 and 0 <= z < 512:
+                want[idx(x, y, z)] = v
+        cells = [idx(x, y, z) for x, y, z in pts if 0 <= x < 512 and 0 <= y < 96 and 0 <= z < 512]
+        assert np.array_equal(lvl2[cells], want[cells])
+        # partial uploads of host data: updatePartialGeometry, a range, a batch of rows
+        host = lvl2.copy()
+        hv = host.reshape(512, 96, 512)
+        hv[300:310, 37:45, 300:312] = 0x777777
+        assert r.updatePartialGeometry((299.0, 36.0, 299.0), (313.0, 46.0, 311.0), host) > 0
+        check_traversal_grid(oracle, r, dims, "updatePartialGeometry")
+        first = 40 + 512 * 38 + 512 * 96 * 60
+        r.uploadRange(first, np.full(3000, 0x00ff00, np.int32))                  # crosses rows of one z slab
+        r.uploadRange(512 * 96 * 70 - 100, np.full(300, -1, np.int32))           # crosses a slab boundary
+        check_traversal_grid(oracle, r, dims, "uploadRange")
+        firsts = np.array([10 + 512 * 37 + 512 * 96 * z for z in range(400, 420)], np.int64)
+        r.uploadRows(firsts, np.full((20, 50), 0x0000ff, np.int32))
+        check_traversal_grid(oracle, r, dims, "uploadRows")
+        path = str(tmp_path / "g.vxg")
+        r.saveGrid(path)
+        r.initVoxels()                                                           # device generator, no depth field: every empty cell is a band cell
+        check_traversal_grid(oracle, r, dims, "initVoxels")
+        r.buildDepthField()
+        assert np.array_equal(check_traversal_grid(oracle, r, dims, "buildDepthField"), default_level)
+        r.loadGrid(path)
+        check_traversal_grid(oracle, r, dims, "loadGrid")
 
 
-@pytest.mark.skipif(os.environ.get("VXRT_TEST_EXPERIMENTS") != "1",
-                    reason="ray.cuh FAST_RUNS experiment: written after round 1's GPU budget was spent, VXRT_TEST_EXPERIMENTS=1 enables it")
-def test_fast_runs_experiment_is_bit_exact(vx, oracle, golden, default_level, monkeypatch):
-    """VXRT_FAST_RUNS=1: shadow / light rays take runs of empty cells without the range tests (ray.cuh).  Same frames, same
-    debug planes, same counters as the oracle; castRay known answers incl. the tie-lock ray and rays next to the faces."""
+def test_traversal_on_and_off_render_the_same_frames(vx, oracle, default_level):
+    """vxrt_set_traversal: rays on the traversal grid vs the plain kernels on the reference-layout grid -- frames, debug planes
+    and counters are those of the oracle both ways; so are castRay's known answers incl. the tie-lock ray"""
     import test_oracle_quirks as q
-    monkeypatch.setenv("VXRT_FAST_RUNS", "1")
-    with vx.Renderer(grid=gc.DIMS, width=160, height=90, debug=True) as r:
-        r.updateGeometry(default_level)
-        for name, W, H in (("C2", 1920, 1080), ("C3ii_pitched", 1280, 720), ("low_sun", 640, 360), ("sparse_lights", 416, 240)):
-            check_frame(vx, oracle, r, default_level, gc.DIMS, gc.frame_cases(W, H)[name], W, H)
-        g = golden["ref_shader"]["kat"]
-        starts, dirs, dists = gc.kat_rays(g["n"], g["seed"])
-        ret, out7 = r.castRays(starts, dirs, dists)
-        assert h64(oracle, ret) == g["ret_fnv"] and h64(oracle, out7) == g["out7_fnv"]
-        ret, out7 = r.castRays(np.array([q.TIE_START] * 2, np.float32), np.array([q.TIE_DIR] * 2, np.float32), np.array([q.TIE_DIST] * 2, np.int32))
-        assert [int(v) for v in ret] == [7391987, 7391987] and out7[1][6] == 61.0
-    # a small grid (every cell within the margin of a face: no run may start) and production frames (counters off)
-    dims = (40, 24, 40)
-    rs = np.random.RandomState(5)
-    level = np.full(dims[0] * dims[1] * dims[2], -1, np.int32)
-    gv = level.reshape(dims[2], dims[1], dims[0])
-    gv[:, :6, :] = 0x406040
-    for _ in range(12):
-        x, y, z = rs.randint(2, 38), rs.randint(6, 16), rs.randint(2, 38)
-        gv[z - 1:z + 2, 6:y, x - 1:x + 2] = int(rs.randint(0, 1 << 24))
-    oracle.compute_depth_field(level, dims)
-    import oracle_lib as ol
-    fr = ol.make_frame((20.0, 14.0, 3.0), aspect=np.float32(16) / np.float32(9), light_pos=(20.0, 120.0, 20.0),
-                       lights=[(8.0 + 6 * i, 9.0, 10.0 + 5 * i, 0.5) for i in range(5)])
-    with vx.Renderer(grid=dims, width=256, height=144, debug=True) as r:
+    W, H = 640, 360
+    level = default_level.copy()
+    with vx.Renderer(grid=gc.DIMS, width=W, height=H, debug=True) as r:
         r.updateGeometry(level)
-        check_frame(vx, oracle, r, level, dims, fr, 256, 144)
-    with vx.Renderer(grid=gc.DIMS, width=640, height=360) as r:        # production variant: no counters, culling on
-        r.updateGeometry(default_level)
-        r.setStats(False)
-        fr = gc.frame_cases(640, 360)["C2"]
-        got = r.renderFrameHost(to_vx_frame(vx, fr))
-        assert np.array_equal(got, oracle.render(default_level, gc.DIMS, fr, 640, 360)["rgba8"])
+        for c in [(200, 40, 180), (195, 37, 190), (210, 50, 200)]:
+            r.removeSphere(c, 7)
+            oracle.remove_sphere(level, gc.DIMS, c[0], c[1], c[2], 7)
+        for on in (True, False):
+            r.setTraversal(on)
+            assert r.traversalActive() == on
+            for name in ("C2", "C3ii_pitched", "low_sun", "C3i"):
+                check_frame(vx, oracle, r, level, gc.DIMS, gc.frame_cases(W, H)[name], W, H)
+            ret, out7 = r.castRays(np.array([q.TIE_START] * 2, np.float32), np.array([q.TIE_DIR] * 2, np.float32), np.array([q.TIE_DIST] * 2, np.int32))
+            rr, hp, hn, st = oracle.cast_ray(level, gc.DIMS, q.TIE_START, q.TIE_DIR, q.TIE_DIST)
+            assert [int(v) for v in ret] == [rr, rr] and out7[0][6] == st and out7[1][6] == st
+    with vx.Renderer(grid=gc.DIMS, width=W, height=H) as r:                    # production kernels (no counters, culling)
+        r.updateGeometry(level)
+        fr = gc.frame_cases(W, H)["C2"]
+        want = oracle.render(level, gc.DIMS, fr, W, H)["rgba8"]
+        for on in (True, False, True):
+            r.setTraversal(on)
+            assert np.array_equal(r.renderFrameHost(to_vx_frame(vx, fr)), want), on
+
+
+def test_values_the_traversal_grid_cannot_encode_fall_back_to_the_plain_kernels(vx, oracle):
+    """a negative value with bit 30 clear (a "jump" shorter than 2: the reference never produces one) cannot be told from a band
+    word: the context then renders from the reference-layout grid -- same pixels as the oracle -- and says so"""
+    dims = (48, 32, 48)
+    lvl = np.full(dims[0] * dims[1] * dims[2], -1, np.int32)
+    gv = lvl.reshape(dims[2], dims[1], dims[0])
+    gv[:, :6, :] = 0x406040
+    oracle.compute_depth_field(lvl, dims)
+    fr = ol.make_frame((24.0, 12.0, 3.0), aspect=np.float32(16) / np.float32(9), light_pos=(24.0, 150.0, 24.0),
+                       lights=[(8.0 + 6 * i, 8.0, 10.0 + 5 * i, 0.5) for i in range(5)])
+    W, H = 192, 108
+    with vx.Renderer(grid=dims, width=W, height=H, debug=True) as r:
+        r.updateGeometry(lvl)
+        assert r.traversalActive()
+        check_frame(vx, oracle, r, lvl, dims, fr, W, H)
+        odd = lvl.copy()
+        odd.reshape(gv.shape)[10:20, 7, 10:30] = np.float32(-1.25).view(np.int32)     # jumps of 1.25
+        r.updateGeometry(odd)
+        assert not r.traversalActive()
+        check_frame(vx, oracle, r, odd, dims, fr, W, H)
+        r.updateGeometry(lvl)                                                    # a full upload starts the count over
+        assert r.traversalActive()
+        r.placeVoxel(5, 8, 5, int(np.float32(-1.5).view(np.int32)))
+        assert not r.traversalActive()
 
 
 # ---- the published configurations at the sizes bench.py publishes (BASELINE.json configs[2..4]) -----------------------

@@ -14,10 +14,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 
-def is_experiment(name):
-    return bool(re.search(r"shade_kernel<\w+, vxrt::GridView(Ref)?, true>|cast_rays_kernel<true>", name))
-
-
 def test_production_kernels_are_the_measured_ones(vx):
     if not (shutil.which("cuobjdump") and shutil.which("c++filt") and shutil.which("nvcc")):
         pytest.skip("cuobjdump / c++filt / nvcc unavailable")

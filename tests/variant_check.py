@@ -1,6 +1,5 @@
-"""Run in a process of its own (tests/test_gpu_parity.py::test_*_in_a_subprocess): frames and known answers of a kernel experiment
-against the oracle -- the FAST_RUNS experiment of ray.cuh (VXRT_FAST_RUNS=1) or a variant library (VXRT_LIB=...), chosen by
-the caller through the environment.  A process of its own because an experiment is new device code: if it faulted, the CUDA
+"""Run in a process of its own: frames and known answers of a kernel experiment against the oracle -- a variant library
+(VXRT_LIB=..., voxel_rt_b200.build.VARIANTS) or the plain kernels (VXRT_TRAVERSAL=0), chosen by the caller through the environment.  A process of its own because an experiment is new device code: if it faulted, the CUDA
 context of the parity tests would be unusable.  Usage: python tests/variant_check.py <label>"""
 import os
 import sys
@@ -19,8 +18,8 @@ import voxel_rt_b200 as vx  # noqa: E402
 
 def main():
     label = sys.argv[1] if len(sys.argv) > 1 else "default"
-    if label == "FAST_RUNS":
-        assert os.environ.get("VXRT_FAST_RUNS") == "1"
+    if label == "no_traversal":
+        assert os.environ.get("VXRT_TRAVERSAL") == "0"
     elif label != "default":
         assert os.path.basename(os.environ.get("VXRT_LIB", "")) == "libvxrt_exp_%s.so" % label, os.environ.get("VXRT_LIB")
     ol.build_oracle()

@@ -63,6 +63,10 @@ _SIGNATURES = {
     "vxrt_load_grid": (C.c_int, [C.c_void_p, C.c_char_p]),
     "vxrt_place_voxel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int32]),
     "vxrt_destroy_voxel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "vxrt_place_voxels": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "vxrt_set_traversal": (C.c_int, [C.c_void_p, C.c_int]),
+    "vxrt_traversal_active": (C.c_int, [C.c_void_p]),
+    "vxrt_download_traversal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "vxrt_edit_remove_sphere": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "vxrt_build_depth_field": (C.c_int, [C.c_void_p]),
     "vxrt_generate_default_level": (C.c_int, [C.c_void_p]),
@@ -270,6 +274,25 @@ class Renderer:
 
     def placeVoxel(self, x, y, z, voxel):
         self._check(self.lib.vxrt_place_voxel(self._h, x, y, z, voxel))
+
+    def placeVoxels(self, xyz, voxels):
+        """a batch of placeVoxel calls (one staged copy + one kernel); xyz [n][3] ints, voxels [n]"""
+        p = np.ascontiguousarray(xyz, np.int32).reshape(-1, 3)
+        v = np.ascontiguousarray(voxels, np.int32).ravel()
+        assert p.shape[0] == v.size
+        self._check(self.lib.vxrt_place_voxels(self._h, v.size, _vp(p), _vp(v)))
+
+    def setTraversal(self, enabled):
+        """rays read the traversal grid (default) or the reference-layout grid with the plain kernels; same pixels"""
+        self._check(self.lib.vxrt_set_traversal(self._h, 1 if enabled else 0))
+
+    def traversalActive(self):
+        return bool(self.lib.vxrt_traversal_active(self._h))
+
+    def downloadTraversal(self):
+        out = np.empty(self.nvox, np.int32)
+        self._check(self.lib.vxrt_download_traversal(self._h, _vp(out), out.size))
+        return out
 
     def destroyVoxel(self, x, y, z):
         self._check(self.lib.vxrt_destroy_voxel(self._h, x, y, z))

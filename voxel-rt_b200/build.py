@@ -101,6 +101,7 @@ VARIANTS = {
     # default library stays exactly what was validated (VXRT_LIB=... pytest -m gpu runs the whole parity suite on one;
     # bench.py's "experiments" object times every entry).  Round 1's late_domain_check is the default now, jump_prefetch
     # (a measured loss) is gone.
+    "late_domain_check": ["-DVXRT_LATE_DOMAIN_CHECK"],      # divide before the fast-domain test of a jump's re-base (ray.cuh)
 }
 
 

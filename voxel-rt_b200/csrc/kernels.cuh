@@ -10,6 +10,7 @@
 //   assemble_kernel  multi-GPU: un-tile the all-gathered per-rank tile buffers into a raster frame
 #pragma once
 #include "ray.cuh"
+#include "trav.cuh"
 
 namespace vxrt {
 
@@ -69,7 +70,8 @@ __device__ __forceinline__ uint32_t out_index_of(const TileMap& m, int raster, i
 // ------------------------------------------------------------------------------------------------
 // COUNT: maintain the per-ray iteration counter (needed by the step-count view, the debug planes and the fetch
 // statistics); the production frame path runs without it.
-template <bool COUNT, class Grid>
+// TRAV: g.vox is the traversal grid (trav.cuh)
+template <bool COUNT, class Grid, bool TRAV>
 __global__ void __launch_bounds__(256, 6) primary_kernel(Grid g, const __grid_constant__ FrameParams f,
                                                       TileMap m, Outputs o) {
     __shared__ unsigned int s_warp_hits[8];
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(256, 6) primary_kernel(Grid g, const __grid_co
         const float rx = __fadd_rn(__fadd_rn(__fmul_rn(M[0], dxn), __fmul_rn(M[4], dyn)), __fadd_rn(__fmul_rn(M[8], dzn), __fmul_rn(M[12], 0.0f)));
         const float ry = __fadd_rn(__fadd_rn(__fmul_rn(M[1], dxn), __fmul_rn(M[5], dyn)), __fadd_rn(__fmul_rn(M[9], dzn), __fmul_rn(M[13], 0.0f)));
         const float rz = __fadd_rn(__fadd_rn(__fmul_rn(M[2], dxn), __fmul_rn(M[6], dyn)), __fadd_rn(__fmul_rn(M[10], dzn), __fmul_rn(M[14], 0.0f)));
-        r = cast_ray<COUNT, false, true>(g, f.cam_pos[0], f.cam_pos[1], f.cam_pos[2], rx, ry, rz, VXRT_RENDER_DIST);   // :139
+        r = cast_ray<COUNT, false, true, Grid, TRAV>(g, f.cam_pos[0], f.cam_pos[1], f.cam_pos[2], rx, ry, rz, VXRT_RENDER_DIST);   // :139
         const uint32_t pid = (uint32_t)(py * m.width + px);
         if (f.view_depth_field == 1) {                               // :143-145
             const float grey = __fdiv_rn((float)r.steps, 100.0f);
@@ -188,8 +190,8 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __rest
     }
 }
 
-// FAST: the shadow / light rays use ray.cuh's FAST_RUNS experiment (unchecked runs of empty cells; off by default)
-template <bool COUNT, class Grid, bool FAST = false>
+// TRAV: g.vox is the traversal grid (trav.cuh): shadow / light rays take the runs its band words promise
+template <bool COUNT, class Grid, bool TRAV>
 __global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_constant__ FrameParams f,
                                                     TileMap m, Outputs o) {
     __shared__ float4 s_light[16];          // compacted active lights (slot order preserved)
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_cons
         if (g_lit || !skip_dark) {   // :154 global-light shadow ray
             if (COUNT) nglobal++;
             normalize3(lx, ly, lz);
-            const RayHit s = cast_ray<COUNT, true, true, Grid, FAST>(g, __fadd_rn(hx, __fmul_rn(lx, 0.001f)), __fadd_rn(hy, __fmul_rn(ly, 0.001f)),
+            const RayHit s = cast_ray<COUNT, true, true, Grid, TRAV>(g, __fadd_rn(hx, __fmul_rn(lx, 0.001f)), __fadd_rn(hy, __fmul_rn(ly, 0.001f)),
                                       __fadd_rn(hz, __fmul_rn(lz, 0.001f)), lx, ly, lz, VXRT_RENDER_DIST);
             fetches += (unsigned)s.steps;
             if (s.idx == -1) multiplier = __fadd_rn(multiplier, __fmul_rn(VXRT_DIFFUSE, max0(dot3(nx, ny, nz, lx, ly, lz))));   // :155
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_cons
                 if (COUNT && !lit) { ndark++; if (skip_dark) continue; }
                 normalize3_with_length(tx, ty, tz, lld);                                    // :173 (same dot, same sqrt as :168)
                 cast |= 2u << slot; nlocal++;
-                const RayHit s = cast_ray<COUNT, true, false, Grid, FAST>(g, __fadd_rn(hx, __fmul_rn(tx, 0.001f)), __fadd_rn(hy, __fmul_rn(ty, 0.001f)),
+                const RayHit s = cast_ray<COUNT, true, false, Grid, TRAV>(g, __fadd_rn(hx, __fmul_rn(tx, 0.001f)), __fadd_rn(hy, __fmul_rn(ty, 0.001f)),
                                           __fadd_rn(hz, __fmul_rn(tz, 0.001f)), tx, ty, tz, f2i(__fadd_rn(lld, 1.0f)));   // :175
                 fetches += (unsigned)s.steps;
                 if (s.idx == -1) {                                                          // :177
@@ -389,6 +391,11 @@ __global__ void __launch_bounds__(256) yrange_kernel(const int32_t* __restrict__
 }
 
 __global__ void set_voxel_kernel(int32_t* vox, long long index, int32_t v) { vox[index] = v; }
+// a batch of placeVoxel calls (distinct cells)
+__global__ void set_voxels_kernel(int32_t* __restrict__ vox, const long long* __restrict__ index, const int32_t* __restrict__ v, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vox[index[i]] = v[i];
+}
 
 // one block per uploaded row: staging holds the rows back to back
 __global__ void scatter_rows_kernel(int32_t* __restrict__ vox, const int32_t* __restrict__ staging,
@@ -399,13 +406,13 @@ __global__ void scatter_rows_kernel(int32_t* __restrict__ vox, const int32_t* __
 }
 
 // known-answer hook: n independent castRay calls
-template <bool FAST = false>
+template <bool TRAV>
 __global__ void cast_rays_kernel(GridView g, int n, const float* __restrict__ starts, const float* __restrict__ dirs,
                                  const int32_t* __restrict__ dists, int32_t* __restrict__ ret, float* __restrict__ out7) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const RayHit r = (i & 1) ? cast_ray<true, true, false, GridView, FAST>(g, starts[3 * i], starts[3 * i + 1], starts[3 * i + 2], dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], dists[i])
-                             : cast_ray<true, false, false>(g, starts[3 * i], starts[3 * i + 1], starts[3 * i + 2], dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], dists[i]);
+    const RayHit r = (i & 1) ? cast_ray<true, true, false, GridView, TRAV>(g, starts[3 * i], starts[3 * i + 1], starts[3 * i + 2], dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], dists[i])
+                             : cast_ray<true, false, false, GridView, TRAV>(g, starts[3 * i], starts[3 * i + 1], starts[3 * i + 2], dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], dists[i]);
     ret[i] = r.idx;
     float nx, ny, nz;
     unpack_normal(r.normal, nx, ny, nz);

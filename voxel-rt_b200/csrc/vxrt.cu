@@ -54,8 +54,13 @@ struct vxrt_ctx {
     cudaEvent_t ev_slot[2] = {nullptr, nullptr};
     bool slot_busy[2] = {false, false};
     unsigned long long submit_seq = 0;
-    // grid
+    // grid: d_vox = the reference-layout master copy (uploads, downloads, edits, depth field); d_trav = the traversal grid the
+    // rays read (trav.cuh), rebuilt over the affected cells after every change to d_vox
     int32_t* d_vox = nullptr;
+    int32_t* d_trav = nullptr;
+    unsigned long long* d_trav_bad = nullptr;
+    unsigned long long trav_bad = 0;    // cells whose value cannot be encoded (then the rays read d_vox with the plain kernels)
+    bool trav_enabled = true;           // vxrt_set_traversal
     size_t nvox = 0;
     bool grid_loaded = false;
     int yrange[2] = {INT_MAX, INT_MIN};  // rows holding solid voxels (never shrinks on destruction: conservative)
@@ -80,7 +85,6 @@ struct vxrt_ctx {
     bool use_tile_order = true;
     bool use_culling = true;
     int l2_prefetch = 2;                // vxrt_set_l2_prefetch: 0 off, 1 on, 2 auto (on when this context renders <= 12,000 tiles)
-    bool fast_runs = false;             // EXPERIMENT (VXRT_FAST_RUNS=1): shadow / light rays use ray.cuh's unchecked runs of empty cells
     int shade_threads = 128;            // threads per shade block (VXRT_SHADE_THREADS: 64 / 128 / 256; 128 measured best)
     int32_t* d_dbg_hit = nullptr;
     uint16_t* d_dbg_steps = nullptr;
@@ -120,9 +124,11 @@ static TileMap make_map(int width, int height, int rank, int world) {
     return m;
 }
 
+static bool use_trav(const vxrt_ctx* c) { return c->trav_enabled && c->trav_bad == 0 && c->d_trav != nullptr; }
+
 static GridView grid_view(const vxrt_ctx* c) {
     GridView g;
-    g.vox = c->d_vox; g.w = c->cfg.grid_w; g.h = c->cfg.grid_h; g.d = c->cfg.grid_d;
+    g.vox = use_trav(c) ? c->d_trav : c->d_vox; g.w = c->cfg.grid_w; g.h = c->cfg.grid_h; g.d = c->cfg.grid_d;
     g.wh = g.w * g.h; g.n = g.w * g.h * g.d;
     g.ymin = c->yrange[0]; g.ymax = c->yrange[1];
     // "every row may hold a solid": nothing is ever culled -- culling switched off, or counted variants that follow the
@@ -238,6 +244,48 @@ static int update_yrange(vxrt_ctx* c, size_t first, size_t count, bool reset) {
     return VXRT_OK;
 }
 
+// ---- traversal grid maintenance ------------------------------------------------------------------------------
+// Rebuild the traversal words of every cell whose word can change when the cells of the box [x0,x1) x [y0,y1) x [z0,z1) of
+// d_vox changed: the box grown by TRAV_REACH in x and z and by one layer downward (a band word looks at most that far).
+// full: the whole grid (the count of values that cannot be encoded starts over).  readback: fetch that count (synchronises).
+static int trav_sync(vxrt_ctx* c, int x0, int y0, int z0, int x1, int y1, int z1, bool full, bool readback) {
+    const int W = c->cfg.grid_w, H = c->cfg.grid_h, D = c->cfg.grid_d;
+    if (full) {
+        x0 = 0; y0 = 0; z0 = 0; x1 = W; y1 = H; z1 = D;
+        CUDA_TRY(cudaMemsetAsync(c->d_trav_bad, 0, sizeof(unsigned long long), c->stream));
+    } else {
+        x0 -= TRAV_REACH; x1 += TRAV_REACH; z0 -= TRAV_REACH; z1 += TRAV_REACH; y0 -= 1;
+    }
+    x0 = std::max(x0, 0); y0 = std::max(y0, 0); z0 = std::max(z0, 0);
+    x1 = std::min(x1, W); y1 = std::min(y1, H); z1 = std::min(z1, D);
+    if (x1 > x0 && y1 > y0 && z1 > z0) {
+        TravBox b{x0, y0, z0, x1 - x0, y1 - y0, z1 - z0};
+        const long long n = (long long)b.nx * b.ny * b.nz;
+        trav_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_vox, c->d_trav, W, H, D, b, c->d_trav_bad);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (readback) {
+        unsigned long long bad = 0;
+        CUDA_TRY(cudaMemcpyAsync(&bad, c->d_trav_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->trav_bad = bad;
+    }
+    return VXRT_OK;
+}
+// the cells of the linear index range [first, first + count)
+static int trav_sync_range(vxrt_ctx* c, size_t first, size_t count, bool readback) {
+    if (count == 0) return VXRT_OK;
+    const size_t W = (size_t)c->cfg.grid_w, WH = W * (size_t)c->cfg.grid_h;
+    const size_t last = first + count - 1;
+    const int z0 = (int)(first / WH), z1 = (int)(last / WH) + 1;
+    int x0 = 0, x1 = (int)W, y0 = 0, y1 = c->cfg.grid_h;
+    if (z1 - z0 == 1) {
+        y0 = (int)((first / W) % (size_t)c->cfg.grid_h); y1 = (int)((last / W) % (size_t)c->cfg.grid_h) + 1;
+        if (y1 - y0 == 1) { x0 = (int)(first % W); x1 = (int)(last % W) + 1; }
+    }
+    return trav_sync(c, x0, y0, z0, x1, y1, z1, false, readback);
+}
+
 static int host_index(const vxrt_config& g, int x, int y, int z) {     // getVoxelIndex render.cpp:189-196
     if (x >= 0 && y >= 0 && z >= 0 && x < g.grid_w && y < g.grid_h && z < g.grid_d)
         return x + g.grid_w * y + g.grid_w * g.grid_h * z;
@@ -307,6 +355,9 @@ extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaStreamCreate failed"));
     for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
     if (cudaMalloc(&c->d_vox, c->nvox * 4) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaMalloc(grid) failed"));
+    if (cudaMalloc(&c->d_trav, c->nvox * 4) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaMalloc(traversal grid) failed"));
+    if (cudaMalloc(&c->d_trav_bad, sizeof(unsigned long long)) != cudaSuccess || cudaMemset(c->d_trav_bad, 0, sizeof(unsigned long long)) != cudaSuccess)
+        return bail(fail(VXRT_ERR_CUDA, "cudaMalloc(traversal counter) failed"));
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaStreamCreate failed"));
     for (auto& e : c->ev_band) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
     for (auto& e : c->ev_band_start) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
@@ -325,7 +376,7 @@ extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     for (int i = 0; i < 4; i++) c->frame.rotate[5 * i] = 1.0f;
     vxrt_init_local_lights(c);
     if (const char* e = getenv("VXRT_L2_PREFETCH")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->l2_prefetch = v; }
-    if (const char* e = getenv("VXRT_FAST_RUNS")) c->fast_runs = atoi(e) == 1;
+    if (const char* e = getenv("VXRT_TRAVERSAL")) c->trav_enabled = atoi(e) != 0;
     if (const char* e = getenv("VXRT_SHADE_THREADS")) {
         const int v = atoi(e);
         if (v == 64 || v == 128 || v == 256) c->shade_threads = v;
@@ -343,7 +394,7 @@ extern "C" void vxrt_destroy(vxrt_ctx* c) {
     if (c->p2p_base) { if (c->p2p_owner) cudaFree(c->p2p_base); else if (!c->p2p_attached) cudaIpcCloseMemHandle(c->p2p_base); }
     cudaFree(c->d_p2p_err);
     cudaFree(c->d_yrange);
-    cudaFree(c->d_vox); cudaFree(c->d_counters); cudaFree(c->d_stage); cudaFree(c->d_first);
+    cudaFree(c->d_vox); cudaFree(c->d_trav); cudaFree(c->d_trav_bad); cudaFree(c->d_counters); cudaFree(c->d_stage); cudaFree(c->d_first);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_first) cudaFreeHost(c->h_first);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -363,6 +414,8 @@ extern "C" int vxrt_upload_grid(vxrt_ctx* c, const int32_t* voxels, size_t count
     CUDA_TRY(cudaMemcpyAsync(c->d_vox, voxels, count * 4, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));      // GL semantics: the caller may modify its array on return
     c->grid_loaded = true;
+    int rc = trav_sync(c, 0, 0, 0, 0, 0, 0, true, true);
+    if (rc != VXRT_OK) return rc;
     return update_yrange(c, 0, c->nvox, true);
 }
 
@@ -372,6 +425,8 @@ extern "C" int vxrt_upload_range(vxrt_ctx* c, size_t first, size_t count, const 
     if (first > c->nvox || count > c->nvox - first) return fail(VXRT_ERR_INVALID, "upload_range: range outside the buffer (GL_INVALID_VALUE)");
     CUDA_TRY(cudaMemcpyAsync(c->d_vox + first, src, count * 4, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    int rc = trav_sync_range(c, first, count, true);
+    if (rc != VXRT_OK) return rc;
     return update_yrange(c, first, count, false);
 }
 
@@ -383,7 +438,27 @@ static int scatter_staged_rows(vxrt_ctx* c, size_t rows, int row_len) {
     CUDA_TRY(cudaMemcpyAsync(c->d_first, c->h_first, rows * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
     scatter_rows_kernel<<<(unsigned)rows, 64, 0, c->stream>>>(c->d_vox, c->d_stage, c->d_first, row_len);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(c->stream));      // staging buffers are reused by the next call
+    {   // traversal words around the rows: one rebuild over their bounding box
+        const size_t W = (size_t)c->cfg.grid_w, WH = W * (size_t)c->cfg.grid_h;
+        int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+        for (size_t r = 0; r < rows; r++) {
+            const size_t f = (size_t)c->h_first[r], l = f + (size_t)row_len - 1;
+            const int z0 = (int)(f / WH), z1 = (int)(l / WH);
+            int y0 = 0, y1 = c->cfg.grid_h - 1, x0 = 0, x1 = (int)W - 1;
+            if (z0 == z1) {
+                y0 = (int)((f / W) % (size_t)c->cfg.grid_h); y1 = (int)((l / W) % (size_t)c->cfg.grid_h);
+                if (y0 == y1) { x0 = (int)(f % W); x1 = (int)(l % W); }
+            }
+            lo[0] = std::min(lo[0], x0); lo[1] = std::min(lo[1], y0); lo[2] = std::min(lo[2], z0);
+            hi[0] = std::max(hi[0], x1); hi[1] = std::max(hi[1], y1); hi[2] = std::max(hi[2], z1);
+        }
+        int rc = trav_sync(c, lo[0], lo[1], lo[2], hi[0] + 1, hi[1] + 1, hi[2] + 1, false, false);
+        if (rc != VXRT_OK) return rc;
+        unsigned long long bad = 0;
+        CUDA_TRY(cudaMemcpyAsync(&bad, c->d_trav_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));  // staging buffers are reused by the next call
+        c->trav_bad = bad;
+    }
     for (size_t r = 0; r < rows; r++)                 // rows uploaded may hold new solids
         for (int i = 0; i < row_len; i++)
             if (c->h_stage[r * (size_t)row_len + i] >= 0) {
@@ -519,6 +594,8 @@ extern "C" int vxrt_load_grid(vxrt_ctx* c, const char* path) {
     if (!ok) return fail(VXRT_ERR_IO, "load_grid: file shorter than its header says");
     if (h != hd.fnv) return fail(VXRT_ERR_IO, "load_grid: payload fingerprint does not match the header");
     c->grid_loaded = true;
+    int rc = trav_sync(c, 0, 0, 0, 0, 0, 0, true, true);
+    if (rc != VXRT_OK) return rc;
     return update_yrange(c, 0, c->nvox, true);
 }
 
@@ -542,6 +619,8 @@ extern "C" int vxrt_download_box(vxrt_ctx* c, const int32_t lo[3], const int32_t
     return VXRT_OK;
 }
 
+static bool unencodable(int32_t v) { return v < 0 && v != -1 && !(v & 0x40000000); }      // see trav.cuh
+
 extern "C" int vxrt_place_voxel(vxrt_ctx* c, int x, int y, int z, int32_t voxel) {      // render.cpp:256-262
     CHECK_CTX(c);
     const int index = host_index(c->cfg, x, y, z);
@@ -549,14 +628,66 @@ extern "C" int vxrt_place_voxel(vxrt_ctx* c, int x, int y, int z, int32_t voxel)
         set_voxel_kernel<<<1, 1, 0, c->stream>>>(c->d_vox, index, voxel);
         CUDA_TRY(cudaGetLastError());
         if (voxel >= 0) { if (y < c->yrange[0]) c->yrange[0] = y; if (y > c->yrange[1]) c->yrange[1] = y; }
+        if (unencodable(voxel)) c->trav_bad++;
+        return trav_sync(c, x, y, z, x + 1, y + 1, z + 1, false, false);
     }
+    return VXRT_OK;
+}
+
+// n placeVoxel calls (render.cpp:256-262; the reference's level code places voxels in bulk: level.cpp:21,74,102,113,124) as one
+// staged copy + one kernel; later entries win where cells repeat, like the sequence of calls would
+extern "C" int vxrt_place_voxels(vxrt_ctx* c, size_t n, const int32_t* xyz, const int32_t* voxels) {
+    CHECK_CTX(c);
+    if (n == 0) return VXRT_OK;
+    if (!xyz || !voxels) return fail(VXRT_ERR_INVALID, "place_voxels: null argument");
+    if (n > (size_t)INT_MAX / 2) return fail(VXRT_ERR_INVALID, "place_voxels: too many voxels");
+    std::vector<long long> idx; std::vector<int32_t> val;
+    idx.reserve(n); val.reserve(n);
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+    for (size_t i = 0; i < n; i++) {
+        const int x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        const int index = host_index(c->cfg, x, y, z);
+        if (index < 0) continue;                                                         // outside the grid: ignored, like placeVoxel
+        idx.push_back(index); val.push_back(voxels[i]);
+        lo[0] = std::min(lo[0], x); lo[1] = std::min(lo[1], y); lo[2] = std::min(lo[2], z);
+        hi[0] = std::max(hi[0], x); hi[1] = std::max(hi[1], y); hi[2] = std::max(hi[2], z);
+        if (voxels[i] >= 0) { if (y < c->yrange[0]) c->yrange[0] = y; if (y > c->yrange[1]) c->yrange[1] = y; }
+        if (unencodable(voxels[i])) c->trav_bad++;
+    }
+    if (idx.empty()) return VXRT_OK;
+    // cells that repeat: keep the last value (a kernel's threads are not ordered)
+    {
+        std::vector<size_t> order(idx.size());
+        for (size_t i = 0; i < order.size(); i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return idx[a] < idx[b]; });
+        std::vector<long long> i2; std::vector<int32_t> v2;
+        for (size_t k = 0; k < order.size(); k++)
+            if (k + 1 == order.size() || idx[order[k + 1]] != idx[order[k]]) { i2.push_back(idx[order[k]]); v2.push_back(val[order[k]]); }
+        idx.swap(i2); val.swap(v2);
+    }
+    const size_t m = idx.size();
+    int rc = ensure_stage(c, m, m);
+    if (rc != VXRT_OK) return rc;
+    memcpy(c->h_stage, val.data(), m * 4);
+    memcpy(c->h_first, idx.data(), m * sizeof(long long));
+    CUDA_TRY(cudaMemcpyAsync(c->d_stage, c->h_stage, m * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_first, c->h_first, m * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    set_voxels_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(c->d_vox, c->d_first, c->d_stage, (long long)m);
+    CUDA_TRY(cudaGetLastError());
+    rc = trav_sync(c, lo[0], lo[1], lo[2], hi[0] + 1, hi[1] + 1, hi[2] + 1, false, false);
+    if (rc != VXRT_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));          // staging buffers are reused by the next call
     return VXRT_OK;
 }
 
 extern "C" int vxrt_destroy_voxel(vxrt_ctx* c, int x, int y, int z) {                   // render.cpp:265-271
     CHECK_CTX(c);
     const int index = host_index(c->cfg, x, y, z);
-    if (x >= 0 && y >= 0 && z >= 0 && index >= 0) { set_voxel_kernel<<<1, 1, 0, c->stream>>>(c->d_vox, index, -1); CUDA_TRY(cudaGetLastError()); }
+    if (x >= 0 && y >= 0 && z >= 0 && index >= 0) {
+        set_voxel_kernel<<<1, 1, 0, c->stream>>>(c->d_vox, index, -1);
+        CUDA_TRY(cudaGetLastError());
+        return trav_sync(c, x, y, z, x + 1, y + 1, z + 1, false, false);
+    }
     return VXRT_OK;
 }
 
@@ -578,7 +709,8 @@ extern "C" int vxrt_edit_remove_sphere(vxrt_ctx* c, int cx, int cy, int cz, int 
     const long long n = (long long)f.nx * f.ny * f.nz;
     depth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_vox, W, H, D, f);
     CUDA_TRY(cudaGetLastError());
-    return VXRT_OK;
+    // the carved cells lie inside the repaired box: traversal words around it, same stream, no synchronisation
+    return trav_sync(c, f.x0, f.y0, f.z0, f.x0 + f.nx, f.y0 + f.ny, f.z0 + f.nz, false, false);
 }
 
 extern "C" int vxrt_build_depth_field(vxrt_ctx* c) {                                     // render.cpp:273-286
@@ -589,8 +721,7 @@ extern "C" int vxrt_build_depth_field(vxrt_ctx* c) {                            
     const long long n = (long long)W * H * D;
     depth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_vox, W, H, D, b);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return VXRT_OK;
+    return trav_sync(c, 0, 0, 0, 0, 0, 0, true, true);               // (synchronises)
 }
 
 // ---- procedural levels ---------------------------------------------------------------------------
@@ -612,7 +743,8 @@ extern "C" int vxrt_generate_default_level(vxrt_ctx* c) {
     CUDA_TRY(cudaGetLastError());
     int rc = launch_trees(c, 36, nullptr, 1);
     if (rc != VXRT_OK) return rc;
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    rc = trav_sync(c, 0, 0, 0, 0, 0, 0, true, true);                  // (synchronises)
+    if (rc != VXRT_OK) return rc;
     c->grid_loaded = true;
     return update_yrange(c, 0, c->nvox, true);
 }
@@ -631,6 +763,8 @@ extern "C" int vxrt_generate_terrain(vxrt_ctx* c, uint64_t seed) {
     int rc = (e == cudaSuccess) ? launch_trees(c, -1, d_surface, 0) : fail(VXRT_ERR_CUDA, cudaGetErrorString(e));
     cudaStreamSynchronize(c->stream);
     cudaFree(d_surface);
+    if (rc != VXRT_OK) return rc;
+    rc = trav_sync(c, 0, 0, 0, 0, 0, 0, true, true);
     if (rc != VXRT_OK) return rc;
     c->grid_loaded = true;
     return update_yrange(c, 0, c->nvox, true);
@@ -699,6 +833,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
     const bool counted_full = c->stats_mode == 1 || (c->stats_mode == 0 && c->d_dbg_hit != nullptr);
     const bool count_primary = count || c->frame.view_depth_field == 1;
     const bool ref_dims = (g.w == GridViewRef::w && g.h == GridViewRef::h && g.d == GridViewRef::d);
+    const bool trav = use_trav(c);
     GridViewRef gr; gr.vox = g.vox; gr.ymin = g.ymin; gr.ymax = g.ymax;
     // bands: whole tile rows when this context owns the whole frame (raster rows stay contiguous), else tile ranges
     const int units = (c->cfg.world == 1) ? c->map.ty : c->map.nlocal;
@@ -724,7 +859,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         const int slab_ints = c->cfg.grid_w * c->cfg.grid_h;
         const int lines_per_slab = (c->cfg.grid_w * ytop + 31) / 32;
         const long long nlines = (long long)lines_per_slab * c->cfg.grid_d;
-        l2_prefetch_kernel<<<148 * 8, 256, 0, c->stream>>>(c->d_vox, lines_per_slab, slab_ints, nlines, c->d_yrange ? c->d_yrange + 2 : nullptr);
+        l2_prefetch_kernel<<<148 * 8, 256, 0, c->stream>>>(g.vox, lines_per_slab, slab_ints, nlines, c->d_yrange ? c->d_yrange + 2 : nullptr);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
     }
@@ -760,13 +895,22 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         o.shade_unit_base = tile0 * upt;
         o.dbg_hit = c->d_dbg_hit; o.dbg_steps = c->d_dbg_steps; o.dbg_occl = c->d_dbg_occl; o.dbg_cast = c->d_dbg_cast;
         const dim3 grid(ntile), block(256);
-        if (ref_dims) {
-            if (count_primary) primary_kernel<true, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, m, o);
-            else primary_kernel<false, GridViewRef><<<grid, block, 0, c->stream>>>(gr, fp, m, o);
-        } else {
-            if (count_primary) primary_kernel<true, GridView><<<grid, block, 0, c->stream>>>(g, fp, m, o);
-            else primary_kernel<false, GridView><<<grid, block, 0, c->stream>>>(g, fp, m, o);
-        }
+        // kernel variants: <iteration counters, grid type (reference extents as compile-time constants / runtime extents), traversal grid>
+#define VXRT_LAUNCH(KERNEL, COUNT, GRID, BLOCK)                                                                              \
+        do {                                                                                                                  \
+            if (ref_dims) {                                                                                                   \
+                if (COUNT) { if (trav) KERNEL<true, GridViewRef, true><<<GRID, BLOCK, 0, c->stream>>>(gr, fp, m, o);          \
+                             else KERNEL<true, GridViewRef, false><<<GRID, BLOCK, 0, c->stream>>>(gr, fp, m, o); }            \
+                else       { if (trav) KERNEL<false, GridViewRef, true><<<GRID, BLOCK, 0, c->stream>>>(gr, fp, m, o);         \
+                             else KERNEL<false, GridViewRef, false><<<GRID, BLOCK, 0, c->stream>>>(gr, fp, m, o); }           \
+            } else {                                                                                                          \
+                if (COUNT) { if (trav) KERNEL<true, GridView, true><<<GRID, BLOCK, 0, c->stream>>>(g, fp, m, o);              \
+                             else KERNEL<true, GridView, false><<<GRID, BLOCK, 0, c->stream>>>(g, fp, m, o); }                \
+                else       { if (trav) KERNEL<false, GridView, true><<<GRID, BLOCK, 0, c->stream>>>(g, fp, m, o);             \
+                             else KERNEL<false, GridView, false><<<GRID, BLOCK, 0, c->stream>>>(g, fp, m, o); }               \
+            }                                                                                                                 \
+        } while (0)
+        VXRT_LAUNCH(primary_kernel, count_primary, grid, block);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
         if (nbands == 1) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -781,19 +925,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         }
         if (c->frame.view_depth_field != 1) {
             const dim3 sblock(c->shade_threads), sgrid((unsigned)(((size_t)ntile * TILE_PIX + c->shade_threads - 1) / c->shade_threads));
-            if (ref_dims) {
-                if (c->fast_runs) {
-                    if (count) shade_kernel<true, GridViewRef, true><<<sgrid, sblock, 0, c->stream>>>(gr, fp, m, o);
-                    else shade_kernel<false, GridViewRef, true><<<sgrid, sblock, 0, c->stream>>>(gr, fp, m, o);
-                } else if (count) shade_kernel<true, GridViewRef><<<sgrid, sblock, 0, c->stream>>>(gr, fp, m, o);
-                else shade_kernel<false, GridViewRef><<<sgrid, sblock, 0, c->stream>>>(gr, fp, m, o);
-            } else {
-                if (c->fast_runs) {
-                    if (count) shade_kernel<true, GridView, true><<<sgrid, sblock, 0, c->stream>>>(g, fp, m, o);
-                    else shade_kernel<false, GridView, true><<<sgrid, sblock, 0, c->stream>>>(g, fp, m, o);
-                } else if (count) shade_kernel<true, GridView><<<sgrid, sblock, 0, c->stream>>>(g, fp, m, o);
-                else shade_kernel<false, GridView><<<sgrid, sblock, 0, c->stream>>>(g, fp, m, o);
-            }
+            VXRT_LAUNCH(shade_kernel, count, sgrid, sblock);
             CUDA_TRY(cudaGetLastError());
             c->launches++;
             if (o.shade_cost && c->map.nlocal >= 64 && refresh_order) {
@@ -856,6 +988,24 @@ extern "C" int vxrt_set_l2_prefetch(vxrt_ctx* c, int enabled) {
 extern "C" int vxrt_set_culling(vxrt_ctx* c, int enabled) {
     if (!c) return fail(VXRT_ERR_INVALID, "null context");
     c->use_culling = enabled != 0;
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_set_traversal(vxrt_ctx* c, int enabled) {
+    if (!c) return fail(VXRT_ERR_INVALID, "null context");
+    c->trav_enabled = enabled != 0;
+    return VXRT_OK;
+}
+
+// 1: the rays read the traversal grid; 0: switched off, or the grid holds values that cannot be encoded (then the plain kernels
+// render from the reference-layout grid: same pixels)
+extern "C" int vxrt_traversal_active(vxrt_ctx* c) { return (c && use_trav(c)) ? 1 : 0; }
+
+extern "C" int vxrt_download_traversal(vxrt_ctx* c, int32_t* out, size_t count) {
+    CHECK_CTX(c);
+    if (!out || count != c->nvox) return fail(VXRT_ERR_INVALID, "download_traversal: count must equal grid_w*grid_h*grid_d");
+    CUDA_TRY(cudaMemcpyAsync(out, c->d_trav, count * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     return VXRT_OK;
 }
 
@@ -1016,7 +1166,7 @@ extern "C" int vxrt_cast_rays(vxrt_ctx* c, int32_t n, const float* starts, const
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dirs, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, dists, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) {
-        if (c->fast_runs) cast_rays_kernel<true><<<(n + 127) / 128, 128, 0, c->stream>>>(grid_view(c), n, d_s, d_d, d_n, d_r, d_o);
+        if (use_trav(c)) cast_rays_kernel<true><<<(n + 127) / 128, 128, 0, c->stream>>>(grid_view(c), n, d_s, d_d, d_n, d_r, d_o);
         else cast_rays_kernel<false><<<(n + 127) / 128, 128, 0, c->stream>>>(grid_view(c), n, d_s, d_d, d_n, d_r, d_o);
         e = cudaGetLastError();
     }
