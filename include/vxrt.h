@@ -128,6 +128,13 @@ int vxrt_place_voxels(vxrt_ctx* ctx, size_t n, const int32_t* xyz, const int32_t
 /* removeSphere(pos, radius) level.cpp:30-56 executed on the device grid (carve + fixDepthField over the
    radius+3 sphere); no host upload needed afterwards */
 int vxrt_edit_remove_sphere(vxrt_ctx* ctx, int cx, int cy, int cz, int radius);
+/* The same edit from a 16-byte command {cx, cy, cz, radius} (4 x int32) in DEVICE memory: queued on the context's stream
+   (vxrt_stream()), the host never reads the command -- in the multi-GPU split (BASELINE configs[4]) the command is the target
+   of ONE NCCL broadcast per edit queued on that stream, and every replica replays it without a host synchronisation.  The
+   kernels are sized for max_radius (<= 64); a command whose radius lies outside [0, max_radius] is refused and
+   vxrt_edit_cmd_error() (which synchronises) returns 1. */
+int vxrt_edit_remove_sphere_cmd(vxrt_ctx* ctx, const int32_t* device_cmd, int max_radius);
+int vxrt_edit_cmd_error(vxrt_ctx* ctx);
 /* computeDepthField sweep over the whole grid, render.cpp:226-253,273-286 (out-of-grid neighbours = solid) */
 int vxrt_build_depth_field(vxrt_ctx* ctx);
 

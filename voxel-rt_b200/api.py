@@ -68,6 +68,8 @@ _SIGNATURES = {
     "vxrt_traversal_active": (C.c_int, [C.c_void_p]),
     "vxrt_download_traversal": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "vxrt_edit_remove_sphere": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vxrt_edit_remove_sphere_cmd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "vxrt_edit_cmd_error": (C.c_int, [C.c_void_p]),
     "vxrt_build_depth_field": (C.c_int, [C.c_void_p]),
     "vxrt_generate_default_level": (C.c_int, [C.c_void_p]),
     "vxrt_generate_terrain": (C.c_int, [C.c_void_p, C.c_uint64]),
@@ -300,6 +302,14 @@ class Renderer:
     def removeSphere(self, pos, radius):
         """level.cpp:30-56 on the device grid."""
         self._check(self.lib.vxrt_edit_remove_sphere(self._h, int(pos[0]), int(pos[1]), int(pos[2]), int(radius)))
+
+    def removeSphereCmd(self, device_cmd_ptr, max_radius=7):
+        """removeSphere from a 16-byte command {cx, cy, cz, r} in device memory (e.g. the target of an NCCL broadcast queued on
+        this context's stream); no host synchronisation"""
+        self._check(self.lib.vxrt_edit_remove_sphere_cmd(self._h, C.c_void_p(int(device_cmd_ptr)), int(max_radius)))
+
+    def editCmdError(self):
+        return self._check(self.lib.vxrt_edit_cmd_error(self._h))
 
     def doDestroy(self, cam_pos, cam_dir, host_voxels=None):
         """controls.cpp:100-110: centre = camPos + 15*camDir, removeSphere(ivec3(centre), 7); instead of

@@ -318,10 +318,7 @@ struct EditBox {
 // render.cpp:226-253 for every cell of the box (optionally restricted to the sphere).  In-place like the
 // reference: writers only turn negative values into other negative values, readers only test the sign.
 // Out-of-grid neighbours count as solid (oracle/vxo.c fix_depth_field_n).
-__global__ void __launch_bounds__(256) depth_kernel(int32_t* __restrict__ vox, int w, int h, int d, EditBox b) {
-    const long long tcount = (long long)b.nx * b.ny * b.nz;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= tcount) return;
+__device__ __forceinline__ void depth_cell(int32_t* __restrict__ vox, int w, int h, int d, const EditBox& b, long long t) {
     const int bx = (int)(t % b.nx), by = (int)((t / b.nx) % b.ny), bz = (int)(t / ((long long)b.nx * b.ny));
     const int x = b.x0 + bx, y = b.y0 + by, z = b.z0 + bz;
     if (x < 0 || y < 0 || z < 0 || x >= w || y >= h || z >= d) return;
@@ -343,6 +340,10 @@ __global__ void __launch_bounds__(256) depth_kernel(int32_t* __restrict__ vox, i
     }
     if (nearest < 0.0f) vox[index] = __float_as_int(nearest);       // :249-251
 }
+__global__ void __launch_bounds__(256) depth_kernel(int32_t* __restrict__ vox, int w, int h, int d, EditBox b) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (long long)b.nx * b.ny * b.nz) depth_cell(vox, w, h, d, b, t);
+}
 
 // level.cpp:31-42: cells of the lopsided sphere become -1 (destroyVoxel render.cpp:265-271)
 __global__ void carve_kernel(int32_t* __restrict__ vox, int w, int h, int d, EditBox b) {
@@ -352,6 +353,34 @@ __global__ void carve_kernel(int32_t* __restrict__ vox, int w, int h, int d, Edi
     if (x < 0 || y < 0 || z < 0 || x >= w || y >= h || z >= d) return;
     const int rx = x - b.cx, ry = y - b.cy, rz = z - b.cz;
     if (rx * rx + ry * ry + rz * rz < b.r2) vox[x + w * y + w * h * z] = -1;
+}
+
+// ---- removeSphere from a 16-byte command in DEVICE memory (multi-GPU: the command arrives by an NCCL broadcast on the render
+// stream, the replicas replay it without the host ever reading it).  cmd = {cx, cy, cz, radius}; the grids are sized for
+// max_r by the host, threads beyond the command's own box retire; a radius outside [0, max_r] is refused (*err = 1).
+__device__ __forceinline__ bool edit_cmd(const int* __restrict__ cmd, int max_r, int& cx, int& cy, int& cz, int& r, int* err) {
+    cx = cmd[0]; cy = cmd[1]; cz = cmd[2]; r = cmd[3];
+    if (r < 0 || r > max_r) { if (blockIdx.x == 0 && threadIdx.x == 0) *err = 1; return false; }
+    return true;
+}
+__global__ void __launch_bounds__(256) carve_cmd_kernel(int32_t* __restrict__ vox, int w, int h, int d, const int* __restrict__ cmd, int max_r, int* err) {
+    int cx, cy, cz, r;
+    if (!edit_cmd(cmd, max_r, cx, cy, cz, r, err) || r == 0) return;
+    const int side = 2 * r, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= side * side * side) return;
+    const int x = cx - r + t % side, y = cy - r + (t / side) % side, z = cz - r + t / (side * side);
+    if (x < 0 || y < 0 || z < 0 || x >= w || y >= h || z >= d) return;
+    const int rx = x - cx, ry = y - cy, rz = z - cz;
+    if (rx * rx + ry * ry + rz * rz < r * r) vox[x + w * y + w * h * z] = -1;          // level.cpp:31-42
+}
+__global__ void __launch_bounds__(256) depth_cmd_kernel(int32_t* __restrict__ vox, int w, int h, int d, const int* __restrict__ cmd, int max_r, int* err) {
+    int cx, cy, cz, r;
+    if (!edit_cmd(cmd, max_r, cx, cy, cz, r, err)) return;
+    const int r2 = r + (7 >> 1), side = 2 * r2;                                        // level.cpp:43
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)side * side * side) return;
+    const EditBox f{cx - r2, cy - r2, cz - r2, side, side, side, cx, cy, cz, r2 * r2};
+    depth_cell(vox, w, h, d, f, t);
 }
 
 // Pull the part of the grid rays can read (rows 0 .. ytop-1 of every z slab) into L2 ahead of the traversal: a frame

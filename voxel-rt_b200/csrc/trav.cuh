@@ -42,12 +42,9 @@ __device__ __forceinline__ int trav_quad_dist(const int32_t* __restrict__ vox, i
     return best;
 }
 
-// one thread per cell of the box (clipped to the grid); *bad += cells whose value cannot be encoded
-__global__ void __launch_bounds__(256) trav_build_kernel(const int32_t* __restrict__ vox, int32_t* __restrict__ trav, int w, int h, int d,
-                                                         TravBox b, unsigned long long* __restrict__ bad) {
-    const long long tcount = (long long)b.nx * b.ny * b.nz;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= tcount) return;
+// the traversal word of one cell of the box (clipped to the grid); *bad += cells whose value cannot be encoded
+__device__ __forceinline__ void trav_cell(const int32_t* __restrict__ vox, int32_t* __restrict__ trav, int w, int h, int d,
+                                          const TravBox& b, long long t, unsigned long long* __restrict__ bad) {
     const int x = b.x0 + (int)(t % b.nx), y = b.y0 + (int)((t / b.nx) % b.ny), z = b.z0 + (int)(t / ((long long)b.nx * b.ny));
     if ((unsigned)x >= (unsigned)w || (unsigned)y >= (unsigned)h || (unsigned)z >= (unsigned)d) return;
     const size_t i = (size_t)x + (size_t)w * y + (size_t)w * h * z;
@@ -67,6 +64,25 @@ __global__ void __launch_bounds__(256) trav_build_kernel(const int32_t* __restri
         word |= (uint32_t)(K | (U << 4)) << (7 * q);
     }
     trav[i] = (int32_t)word;
+}
+
+// one thread per cell of the box
+__global__ void __launch_bounds__(256) trav_build_kernel(const int32_t* __restrict__ vox, int32_t* __restrict__ trav, int w, int h, int d,
+                                                         TravBox b, unsigned long long* __restrict__ bad) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (long long)b.nx * b.ny * b.nz) trav_cell(vox, trav, w, h, d, b, t, bad);
+}
+
+// the rebuild that follows a removeSphere whose command {cx, cy, cz, radius} lives in device memory (kernels.cuh *_cmd_kernel):
+// the repaired sphere's box grown by TRAV_REACH in x and z and by one layer downward; the grid is sized for max_r by the host
+__global__ void __launch_bounds__(256) trav_cmd_kernel(const int32_t* __restrict__ vox, int32_t* __restrict__ trav, int w, int h, int d,
+                                                       const int* __restrict__ cmd, int max_r, unsigned long long* __restrict__ bad) {
+    const int r = cmd[3];
+    if (r < 0 || r > max_r) return;
+    const int r2 = r + (7 >> 1);
+    const TravBox b{cmd[0] - r2 - TRAV_REACH, cmd[1] - r2 - 1, cmd[2] - r2 - TRAV_REACH, 2 * (r2 + TRAV_REACH), 2 * r2 + 1, 2 * (r2 + TRAV_REACH)};
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (long long)b.nx * b.ny * b.nz) trav_cell(vox, trav, w, h, d, b, t, bad);
 }
 
 }  // namespace vxrt

@@ -64,7 +64,8 @@ struct vxrt_ctx {
     size_t nvox = 0;
     bool grid_loaded = false;
     int yrange[2] = {INT_MAX, INT_MIN};  // rows holding solid voxels (never shrinks on destruction: conservative)
-    int* d_yrange = nullptr;
+    int* d_yrange = nullptr;            // [0..1] the range, [2] sink of the L2 sweep, [3] "a device-side edit command was refused"
+    bool edit_err_zeroed = false;
     // frame state
     vxrt_frame frame{};
     TileMap map{};
@@ -711,6 +712,42 @@ extern "C" int vxrt_edit_remove_sphere(vxrt_ctx* c, int cx, int cy, int cz, int 
     CUDA_TRY(cudaGetLastError());
     // the carved cells lie inside the repaired box: traversal words around it, same stream, no synchronisation
     return trav_sync(c, f.x0, f.y0, f.z0, f.x0 + f.nx, f.y0 + f.ny, f.z0 + f.nz, false, false);
+}
+
+// removeSphere whose 16-byte command {cx, cy, cz, radius} lives in DEVICE memory (e.g. the target of an NCCL broadcast queued on
+// vxrt_stream()): queued behind it on the context's stream, the host never reads the command.  radius must be in [0, max_radius].
+extern "C" int vxrt_edit_remove_sphere_cmd(vxrt_ctx* c, const int32_t* device_cmd, int max_radius) {
+    CHECK_CTX(c);
+    if (!device_cmd) return fail(VXRT_ERR_INVALID, "remove_sphere_cmd: null command");
+    if (max_radius < 0 || max_radius > 64) return fail(VXRT_ERR_INVALID, "remove_sphere_cmd: max_radius must be in [0, 64]");
+    if (!c->grid_loaded) return fail(VXRT_ERR_STATE, "remove_sphere_cmd before any grid upload");
+    if (!c->d_yrange) CUDA_TRY(cudaMalloc(&c->d_yrange, 4 * sizeof(int)));
+    const int W = c->cfg.grid_w, H = c->cfg.grid_h, D = c->cfg.grid_d;
+    int* err = c->d_yrange + 3;
+    if (!c->edit_err_zeroed) { CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), c->stream)); c->edit_err_zeroed = true; }
+    if (max_radius > 0) {
+        const long long n = 8ll * max_radius * max_radius * max_radius;
+        carve_cmd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_vox, W, H, D, device_cmd, max_radius, err);
+        CUDA_TRY(cudaGetLastError());
+    }
+    const int r2 = max_radius + (7 >> 1);
+    const long long nd = 8ll * r2 * r2 * r2;
+    depth_cmd_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, c->stream>>>(c->d_vox, W, H, D, device_cmd, max_radius, err);
+    CUDA_TRY(cudaGetLastError());
+    const long long nt = 4ll * (r2 + TRAV_REACH) * (r2 + TRAV_REACH) * (2 * r2 + 1);
+    trav_cmd_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, c->stream>>>(c->d_vox, c->d_trav, W, H, D, device_cmd, max_radius, c->d_trav_bad);
+    CUDA_TRY(cudaGetLastError());
+    return VXRT_OK;
+}
+
+// 1 if a device-side edit command was refused since the context was created (radius outside [0, max_radius]); synchronises
+extern "C" int vxrt_edit_cmd_error(vxrt_ctx* c) {
+    CHECK_CTX(c);
+    if (!c->d_yrange || !c->edit_err_zeroed) return 0;
+    int e = 0;
+    CUDA_TRY(cudaMemcpyAsync(&e, c->d_yrange + 3, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return e;
 }
 
 extern "C" int vxrt_build_depth_field(vxrt_ctx* c) {                                     // render.cpp:273-286
