@@ -228,18 +228,27 @@ def run_b200(args):
 
     p2p_state = {"ptr": 0, "hold": False}
 
+    edits_dev = edit_cmd = None
+    if edits is not None and world > 1:
+        # only rank 0 knows the edits (it is the one with the mouse); every other rank sees them through the broadcast alone
+        e4 = np.concatenate([edits, np.full((len(edits), 1), 7, np.int32)], axis=1) if rank == 0 else np.zeros((len(edits), 4), np.int32)
+        edits_dev = torch.from_numpy(np.ascontiguousarray(e4)).to("cuda")
+        edit_cmd = torch.zeros(4, dtype=torch.int32, device="cuda")
+
     def apply_edit():
         if edits is not None:                                     # C5: right-click destruction before every frame
             k = edit_state["k"] % len(edits)
             edit_state["k"] += 1
-            if world > 1:                                         # rank 0 decides, the 16-byte command is broadcast (NCCL)
-                cmd = torch.tensor([int(edits[k][0]), int(edits[k][1]), int(edits[k][2]), 7] if rank == 0 else [0, 0, 0, 0],
-                                   dtype=torch.int32, device="cuda")
-                dist.broadcast(cmd, src=0)
-                c = cmd.tolist()
+            if world > 1:
+                # rank 0 decides; the 16-byte command {cx, cy, cz, r} goes out as ONE NCCL broadcast queued on the render stream and
+                # every replica replays it from device memory (vxrt_edit_remove_sphere_cmd): no host synchronisation anywhere
+                with torch.cuda.stream(stream):
+                    if rank == 0:
+                        edit_cmd.copy_(edits_dev[k], non_blocking=True)
+                    dist.broadcast(edit_cmd, src=0)
+                ren.removeSphereCmd(edit_cmd.data_ptr(), 7)
             else:
-                c = [int(edits[k][0]), int(edits[k][1]), int(edits[k][2]), 7]
-            ren.removeSphere(c[:3], c[3])
+                ren.removeSphere([int(edits[k][0]), int(edits[k][1]), int(edits[k][2])], 7)
 
     def flush_l2():
         with torch.cuda.stream(stream):
@@ -282,11 +291,23 @@ def run_b200(args):
         ev[k][1].record(stream)
         if k % 8 == 7 or k == args.steps - 1:
             ren.sync()
-        # per-kernel CUDA-event durations of this frame (events live inside vxrt_render, same stream)
-        if k % 8 == 7 or k == args.steps - 1:
+            # per-kernel CUDA-event durations of this frame (events live inside vxrt_render, same stream)
             s = ren.stats(); kern_ms["primary"].append(s["ms_primary"]); kern_ms["shade"].append(s["ms_shadow"])
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    kern_ms_source = "CUDA events inside vxrt_render, frames of the timed region"
+    if frame.view_depth_field != 1 and max(kern_ms["shade"]) == 0.0:
+        # the two passes overlap in this configuration (vxrt_set_overlap, auto): their separate durations come from the same frames
+        # rendered once more with the overlap switched off
+        kern_ms = {"primary": [], "shade": []}
+        ren.setOverlap(0)
+        for k in range(2 + min(args.steps, 10)):
+            flush_l2(); step_device(); ren.sync()
+            if k >= 2:
+                s = ren.stats(); kern_ms["primary"].append(s["ms_primary"]); kern_ms["shade"].append(s["ms_shadow"])
+        ren.setOverlap(2)
+        kern_ms_source = "CUDA events inside vxrt_render, the timed region's frames rendered again with the overlap of the two passes off (the timed region itself overlaps them)"
+    barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
     # MAX over ranks of the summed device time; rays / fetches summed over ranks
@@ -311,6 +332,20 @@ def run_b200(args):
     # (every ray fshader.glsl casts for this frame, incl. the unlit ones whose term is exactly 0) is reported beside it
     value = rays_traced / (ms_per_step * 1e-3) / 1e6
     value_ref_rule = rays / (ms_per_step * 1e-3) / 1e6
+
+    # C5: what one edit costs on its own (carve + depth-field repair + traversal-grid repair, and for N > 1 the broadcast of its
+    # command), CUDA events around the edit alone, max over ranks
+    edit_ms = None
+    if edits is not None:
+        ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]
+        for a, b in ee:
+            a.record(stream); apply_edit(); b.record(stream)
+        barrier()
+        edit_ms = float(sum(a.elapsed_time(b) for a, b in ee)) / len(ee)
+        if world > 1:
+            t = torch.tensor([edit_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            edit_ms = float(t.item())
 
     # ---- e2e: the public C-ABI call with HOST buffers (frame params in, RGBA8 frame out), wall clock ----
     host_out = ren.hostFrameBuffer()                              # page-locked (vxrt_host_alloc)
@@ -537,6 +572,7 @@ def run_b200(args):
                 continue
         roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s",
                     "frac": round(achieved / hbm, 5), "traffic": traffic, "peak_source": peak_src,
+                    "kernel_times": kern_ms_source,
                     "achieved_with_reference_iterations": round(achieved_ref, 2), "frac_with_reference_iterations": round(achieved_ref / hbm, 5),
                     "issue": issue,
                     "note": "HBM bookkeeping figure: algorithmic bytes (4 B x castRay iterations the kernel executes + colour read + RGBA8 store, rank 0's "
@@ -586,7 +622,12 @@ def run_b200(args):
             result["parity"] = parity_check(frame, parity_frame, level_arr if parity_level is None else parity_level, grid, W, H,
                                             stride=4 if scene != "C4" else 16)
         if scene == "C5":
-            result["config"]["edits"] = "one vxrt_edit_remove_sphere(r=7) per frame, centres from mt19937(12345); rays/fetches are those of the last frame"
+            result["config"]["edits"] = ("one removeSphere(r=7) per frame, centres from mt19937(12345); rays/fetches are those of the counted frames; "
+                                         + ("N > 1: rank 0's 16-byte command is one NCCL broadcast per edit on the render stream, every replica replays it "
+                                            "from device memory (vxrt_edit_remove_sphere_cmd), no host synchronisation" if world > 1 else
+                                            "vxrt_edit_remove_sphere (device edit: carve + depth-field repair + traversal-grid repair, no upload)"))
+            result["config"]["ms_per_edit"] = round(edit_ms, 4) if edit_ms is not None else None
+            result["config"]["edit_cmd_error"] = int(ren.editCmdError()) if world > 1 else 0
         if not args.no_extra and world == 1 and scene not in ("C4", "C5"):
             production_fnv = "%016x" % vx.scenes.fnv1a64(host_out)          # the frame the e2e loop delivered
             result["other_workloads"] = extra_workloads(vx, ren, flush_l2, stream, torch)
@@ -598,7 +639,7 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
         del gathered, final, local_t
-    del flush, final_host
+    del flush, final_host, edits_dev, edit_cmd
     p2p_err = ren.p2pError() if use_p2p else 0
     if p2p_err:
         raise SystemExit("peer-memory wait timed out (code %d)" % p2p_err)

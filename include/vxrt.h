@@ -188,6 +188,13 @@ int vxrt_download_traversal(vxrt_ctx* ctx, int32_t* out, size_t count);
 /* enabled (default): the primary pass records how long each tile's block took and the next frame launches the
    slowest tiles first (shorter kernel tail; it matters when a GPU renders only a fraction of the frame).  Same pixels. */
 int vxrt_set_tile_ordering(vxrt_ctx* ctx, int enabled);
+/* Overlap of the two passes of a frame: 0 off, 1 on, 2 auto (default: on when this context renders <= 12,000 tiles, i.e. a
+   1080p frame or a share of a 4K frame -- where the serial tail of the primary pass's longest rays, not throughput, sets the
+   time).  On: the shade kernel is launched with programmatic stream serialization and the primary kernel releases it at once
+   (griddepcontrol.launch_dependents), so shade blocks are scheduled into the SM capacity the primary pass's tail leaves idle;
+   a shade block waits for ITS tile's ready flag (release / acquire, bounded spin) instead of the kernel boundary.  Same
+   pixels.  While on, vxrt_get_stats cannot separate the passes: ms_primary reads as the whole frame, ms_shadow as 0. */
+int vxrt_set_overlap(vxrt_ctx* ctx, int mode);
 /* mode 0 (default) = the production kernels: no per-iteration counter, rays that cannot change a pixel are not traced
    (vxrt_set_culling); vxrt_get_stats then reads rays_local / fetches / rays_dark as 0 while hit_pixels, rays_primary,
    rays_global and the timings stay valid.  mode 1: every vxrt_render runs the counted kernel variants by the REFERENCE's

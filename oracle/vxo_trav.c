@@ -229,3 +229,132 @@ void vxo_trav_render(const int32_t* trav, vxo_dims g, const vxo_frame* f, int wi
     if (counters) for (int k = 0; k < 5; k++) counters[k] += tot[k];
     if (stats9) for (int k = 0; k < 3; k++) { stats9[k] += tsum.steps_fast[k]; stats9[3 + k] += tsum.steps_checked[k]; stats9[6 + k] += tsum.jumps[k]; }
 }
+
+/* ---- analysis only: how long are the runs under other caps / encodings?  (scripts/where_iterations_go.py --trav-study) -------
+ * The promise of every -1 cell is kept UNPACKED (one byte per quadrant for K, one for U), so that caps beyond what fits the 30
+ * payload bits of a band word can be tried.  ucode7: U is stored in 3 bits as {0..6, 7 = "U equals K"} (anything between 7 and K - 1
+ * is stored as 6).  Rays from surfaces that face away from their light are left out (the production kernels do not trace them). */
+typedef struct { const uint8_t* K; const uint8_t* U; trav_stats ts; uint64_t runs[3]; } study_ctx;
+
+static int32_t cast_ray_study(const int32_t* vox, vxo_dims g, vxo_shader_state* st, float sx, float sy, float sz, float rx, float ry, float rz,
+                              int32_t dist, study_ctx* S, int kind) {
+    int32_t cx = vxo_f2i(sx), cy = vxo_f2i(sy), cz = vxo_f2i(sz);
+    int32_t fColorIndex = -1, tempIndex = -1;
+    int32_t stepx = vxo_f2i(vxo_fsign(rx)), stepy = vxo_f2i(vxo_fsign(ry)), stepz = vxo_f2i(vxo_fsign(rz));
+    int32_t fwx = (stepx > 0), fwy = (stepy > 0), fwz = (stepz > 0);
+    float dx = 1.0f / fabsf(rx + 0.000001f), dy = 1.0f / fabsf(ry + 0.000001f), dz = 1.0f / fabsf(rz + 0.000001f);
+    float ix = ((float)(int32_t)((uint32_t)cx + (uint32_t)fwx) - sx) / rx;
+    float iy = ((float)(int32_t)((uint32_t)cy + (uint32_t)fwy) - sy) / ry;
+    float iz = ((float)(int32_t)((uint32_t)cz + (uint32_t)fwz) - sz) / rz;
+    float currDist = 0.0f, distTravelled = 0.0f;
+    const int q = (stepx > 0) | ((stepz > 0) << 1), up = stepy > 0;
+    int K = 0, E = TRAV_BIG;
+    while (distTravelled < (float)dist && distTravelled < (float)VXO_RENDER_DIST) {
+        st->stepCount = st->stepCount + 1.0f;
+        st->fetches++;
+        const int bx = ix < iy && ix < iz, by = !bx && (iy < ix && iy < iz);
+        const int in_run = K >= 1 && (!by || K - E >= 1);
+        distTravelled = distTravelled + 1.0f;
+        if (bx) { currDist = ix; cx = (int32_t)((uint32_t)cx + (uint32_t)stepx); ix = ix + dx; }
+        else if (by) { currDist = iy; cy = (int32_t)((uint32_t)cy + (uint32_t)stepy); iy = iy + dy; }
+        else { currDist = iz; cz = (int32_t)((uint32_t)cz + (uint32_t)stepz); iz = iz + dz; }
+        st->hitNormal[0] = bx ? (float)(-stepx) : 0.0f; st->hitNormal[1] = by ? (float)(-stepy) : 0.0f; st->hitNormal[2] = (!bx && !by) ? (float)(-stepz) : 0.0f;
+        if (in_run) {
+            if (by) { K = K - E - 1; E = TRAV_BIG; } else K--;
+            S->ts.steps_fast[kind]++;
+            continue;
+        }
+        S->ts.steps_checked[kind]++;
+        tempIndex = vxo_shader_index(g, cx, cy, cz);
+        K = 0; E = TRAV_BIG;
+        if (tempIndex < 0) break;
+        const int32_t w = vox[tempIndex];
+        if (w >= 0) {
+            st->hitPos[0] = rx * currDist + sx; st->hitPos[1] = ry * currDist + sy; st->hitPos[2] = rz * currDist + sz;
+            fColorIndex = tempIndex;
+            break;
+        } else if (w == -1) {
+            K = S->K[(size_t)tempIndex * 4 + q];
+            const int U = up ? S->U[(size_t)tempIndex * 4 + q] : 0;
+            E = K - U;
+            if (K >= 1) S->runs[kind]++;
+        } else {
+            float bits; memcpy(&bits, &w, 4);
+            float toJump = -bits;
+            distTravelled = distTravelled + toJump;
+            currDist = currDist + toJump;
+            sx = rx * currDist + sx; sy = ry * currDist + sy; sz = rz * currDist + sz;
+            cx = vxo_f2i(sx); cy = vxo_f2i(sy); cz = vxo_f2i(sz);
+            ix = ((float)(int32_t)((uint32_t)cx + (uint32_t)fwx) - sx) / rx;
+            iy = ((float)(int32_t)((uint32_t)cy + (uint32_t)fwy) - sy) / ry;
+            iz = ((float)(int32_t)((uint32_t)cz + (uint32_t)fwz) - sz) / rz;
+            S->ts.jumps[kind]++;
+        }
+    }
+    return fColorIndex;
+}
+
+/* the plain restatement for the rays the study leaves out */
+#define VXO_CAST_RAY_NAME cast_ray_plain_copy
+#define VXO_HOOK_ARGS
+#define VXO_HOOK_START()
+#define VXO_HOOK_ITER()
+#define VXO_HOOK_JUMP()
+#define VXO_HOOK_END(outcome)
+#include "vxo_castray_body.inc"
+
+static int32_t study_adapter(void* user, const int32_t* vox, vxo_dims g, vxo_shader_state* st, float sx, float sy, float sz,
+                             float rx, float ry, float rz, int32_t dist, int kind, int dark) {
+    if (dark) return cast_ray_plain_copy(vox, g, st, sx, sy, sz, rx, ry, rz, dist);
+    return cast_ray_study(vox, g, st, sx, sy, sz, rx, ry, rz, dist, (study_ctx*)user, kind);
+}
+
+/* out12: run steps, checked steps, jumps, runs started -- per ray kind 0 / 1 / 2; returns the number of pixels that differ from
+ * vxo_render (must be 0) */
+int64_t vxo_trav_study(const int32_t* vox, vxo_dims g, const vxo_frame* f, int width, int height, int kcap, int ucap, int ucode7, uint64_t out12[12]) {
+    const size_t n = (size_t)g.w * g.h * g.d;
+    uint8_t* Kb = (uint8_t*)calloc(n * 4, 1);
+    uint8_t* Ub = (uint8_t*)calloc(n * 4, 1);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int z = 0; z < g.d; z++)
+        for (int y = 0; y < g.h; y++)
+            for (int x = 0; x < g.w; x++) {
+                const size_t i = (size_t)x + (size_t)g.w * y + (size_t)g.w * g.h * z;
+                if (vox[i] != -1) continue;
+                for (int q = 0; q < 4; q++) {
+                    const int sx = (q & 1) ? 1 : -1, sz = (q & 2) ? 1 : -1;
+                    const int K = quad_dist(vox, g, x, y, z, sx, sz, kcap + 1) - 1;
+                    int U = quad_dist(vox, g, x, y + 1, z, sx, sz, ucode7 ? kcap : ucap);
+                    if (U > K) U = K;
+                    if (ucode7 && U < K && U > 6) U = 6;
+                    Kb[i * 4 + q] = (uint8_t)K; Ub[i * 4 + q] = (uint8_t)U;
+                }
+            }
+    int64_t bad = 0;
+    uint64_t tot[12] = {0};
+#ifdef _OPENMP
+#pragma omp parallel reduction(+ : bad)
+#endif
+    {
+        study_ctx S; memset(&S, 0, sizeof S); S.K = Kb; S.U = Ub;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4)
+#endif
+        for (int py = 0; py < height; py++)
+            for (int px = 0; px < width; px++) {
+                float a[4], b[4];
+                vxo_shade_pixel_with(study_adapter, &S, vox, g, f, width, height, px, py, a, NULL, NULL, NULL, NULL, NULL, NULL, NULL);
+                vxo_shade_pixel(vox, g, f, width, height, px, py, b, NULL, NULL, NULL, NULL, NULL, NULL, NULL);
+                if (memcmp(a, b, sizeof a)) bad++;
+            }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        for (int k = 0; k < 3; k++) { tot[k] += S.ts.steps_fast[k]; tot[3 + k] += S.ts.steps_checked[k]; tot[6 + k] += S.ts.jumps[k]; tot[9 + k] += S.runs[k]; }
+    }
+    for (int k = 0; k < 12; k++) out12[k] = tot[k];
+    free(Kb); free(Ub);
+    return bad;
+}

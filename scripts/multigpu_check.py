@@ -81,11 +81,23 @@ def main():
     got = render_frame()
     got_p2p = render_frame_p2p(5)                  # 5 frames > 2 buffers: exercises the back-pressure across processes
     # edit broadcast: rank 0 picks the edits, every replica applies the same commands
-    edits = torch.tensor(vx.scenes.edit_centres(8) if rank == 0 else np.zeros((8, 3), np.int32), dtype=torch.int32, device="cuda")
+    # ren: every edit is a 16-byte command {cx, cy, cz, r} known to rank 0 only, ONE NCCL broadcast per edit queued on the render
+    # stream, replayed from device memory on every replica (vxrt_edit_remove_sphere_cmd; no host synchronisation);
+    # ren2: the whole list broadcast ahead, host-argument edits
+    e4 = np.concatenate([vx.scenes.edit_centres(8), np.full((8, 1), 7, np.int32)], axis=1)
+    edits = torch.tensor(e4 if rank == 0 else np.zeros((8, 4), np.int32), dtype=torch.int32, device="cuda")
+    cmd = torch.zeros(4, dtype=torch.int32, device="cuda")
+    for k in range(8):
+        with torch.cuda.stream(stream):
+            if rank == 0:
+                cmd.copy_(edits[k], non_blocking=True)
+            dist.broadcast(cmd, src=0)
+        ren.removeSphereCmd(cmd.data_ptr(), 7)
+    ren.sync()
+    cmd_err = ren.editCmdError()
     dist.broadcast(edits, src=0)
     for c in edits.cpu().numpy():
-        ren.removeSphere(c, 7)
-        ren2.removeSphere(c, 7)
+        ren2.removeSphere(c[:3], int(c[3]))
     got_edit = render_frame()
     got_edit_p2p = render_frame_p2p(3)
     # pipelined owner read-back: 6 frames queued back to back, alternating host buffers
@@ -125,6 +137,8 @@ def main():
     fnv = vx.scenes.fnv1a64(ren.downloadGrid())
     fnvs = [None] * world
     dist.all_gather_object(fnvs, fnv)
+    tfnvs = [None] * world
+    dist.all_gather_object(tfnvs, (vx.scenes.fnv1a64(ren.downloadTraversal()), vx.scenes.fnv1a64(ren2.downloadTraversal()), cmd_err))
     if rank == 0:
         import ctypes as C
         import conftest
@@ -151,9 +165,14 @@ def main():
         print("frames stored straight into the shared host frame vs gathered frame:", host_ok)
         ok &= all(f == o.fnv(level) for f in fnvs)
         print("replica fingerprints equal oracle:", all(f == o.fnv(level) for f in fnvs), ["%016x" % f for f in fnvs])
+        want_trav, bad = o.trav_build(level, (512, 96, 512))
+        tf = o.fnv(want_trav)
+        trav_ok = bad == 0 and all(t[0] == tf and t[1] == tf and t[2] == 0 for t in tfnvs)
+        ok &= trav_ok
+        print("traversal grids of every replica (device-command edits and host-argument edits) equal the host rebuild:", trav_ok)
     dist.barrier()
     dist.destroy_process_group()
-    del gathered, final, local_t, final2, handle
+    del gathered, final, local_t, final2, handle, cmd, edits
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     ren.close()

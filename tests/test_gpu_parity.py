@@ -945,3 +945,74 @@ def test_stats_modes_count_the_reference_rule_and_the_executed_work(vx, oracle, 
             assert st[2]["hit_pixels"] == c[4] and st[2]["rays_primary"] == c[0]
             with pytest.raises(vx.VxrtError):
                 r.setStats(3)
+
+
+def test_overlapped_passes_render_the_same_frames(vx, oracle, default_level):
+    """vxrt_set_overlap: the shade kernel is launched with programmatic stream serialization and starts inside the primary pass's
+    tail; its blocks wait for their tile's ready flag.  Same pixels as the oracle for production and counted kernels, across
+    frames that differ (a stale flag or hit slot would show), frame sizes, launch orders and a tile-partition context"""
+    level = default_level
+    for W, H in ((640, 360), (1920, 1080), (100, 37)):
+        names = ["C2", "C3ii_pitched", "low_sun", "C3i", "sparse_lights", "C2"]
+        want = {n: oracle.render(level, gc.DIMS, gc.frame_cases(W, H)[n], W, H)["rgba8"] for n in set(names)}
+        with vx.Renderer(grid=gc.DIMS, width=W, height=H) as r:
+            r.updateGeometry(level)
+            out = r.hostFrameBuffer()
+            for mode in (1, 0, 2):
+                r.setOverlap(mode)
+                for stats in (0, 1):
+                    r.setStats(stats)
+                    for k, n in enumerate(names * 2):
+                        r.updateUniforms(to_vx_frame(vx, gc.frame_cases(W, H)[n]))
+                        r.draw()                                             # whole-frame launch: the overlapped path
+                        got = r.readPixels()
+                        bad = int((got != want[n]).any(axis=2).sum())
+                        assert bad == 0, (W, H, mode, stats, k, n, bad)
+            r.setStats(0)
+            r.setOverlap(1)
+            out[:] = 0x5A
+            r.renderFrameHost(to_vx_frame(vx, gc.frame_cases(W, H)["C2"]), out)   # banded path: not overlapped, same pixels
+            assert np.array_equal(out, want["C2"])
+    W, H, world = 1280, 720, 4
+    fr = gc.frame_cases(W, H)["C3ii_pitched"]
+    want = oracle.render(level, gc.DIMS, fr, W, H)["rgba8"]
+    parts = []
+    for rank in range(world):
+        with vx.Renderer(grid=gc.DIMS, width=W, height=H, rank=rank, world=world) as r:
+            r.updateGeometry(level)
+            r.setOverlap(1)
+            r.updateUniforms(to_vx_frame(vx, fr))
+            for _ in range(3):
+                r.draw()
+            parts.append(r.readPixels())
+    assert np.array_equal(vx.tiles.assemble(np.stack(parts), W, H), want)
+
+
+def test_remove_sphere_from_a_device_side_command(vx, oracle, default_level):
+    """vxrt_edit_remove_sphere_cmd: the 16-byte command {cx, cy, cz, r} lives in device memory (in the multi-GPU split it is the
+    target of an NCCL broadcast on the render stream); the grid and its traversal grid must end up as after the host-argument
+    edit / the oracle's removeSphere; a radius beyond max_radius is refused and reported"""
+    import torch
+    level = default_level.copy()
+    rs = np.random.RandomState(23)
+    with vx.Renderer(grid=gc.DIMS, width=32, height=8) as r:
+        r.updateGeometry(level)
+        stream = torch.cuda.ExternalStream(r.stream_ptr())
+        cmd = torch.zeros(4, dtype=torch.int32, device="cuda")
+        for k in range(8):
+            c = [int(rs.randint(-2, 514)), int(rs.randint(28, 48)), int(rs.randint(-2, 514)), int(rs.randint(0, 8))]
+            with torch.cuda.stream(stream):
+                cmd.copy_(torch.tensor(c, dtype=torch.int32), non_blocking=False)
+            r.removeSphereCmd(cmd.data_ptr(), 7)
+            r.sync()
+            oracle.remove_sphere(level, gc.DIMS, *c)
+        got = check_traversal_grid(oracle, r, gc.DIMS, "device-side commands")
+        assert h64(oracle, got) == h64(oracle, level)
+        assert r.editCmdError() == 0
+        with torch.cuda.stream(stream):
+            cmd.copy_(torch.tensor([100, 40, 100, 9], dtype=torch.int32))
+        r.removeSphereCmd(cmd.data_ptr(), 7)                                     # radius 9 > max_radius 7: refused, nothing changes
+        assert r.editCmdError() == 1
+        assert h64(oracle, r.downloadGrid()) == h64(oracle, level)
+        del cmd
+        torch.cuda.synchronize()

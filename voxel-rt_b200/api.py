@@ -85,6 +85,7 @@ _SIGNATURES = {
     "vxrt_set_l2_prefetch": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_culling": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_tile_ordering": (C.c_int, [C.c_void_p, C.c_int]),
+    "vxrt_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_render_frame_host": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p]),
     "vxrt_submit_frame_host": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p]),
@@ -383,6 +384,10 @@ class Renderer:
 
     def setCulling(self, enabled):
         self._check(self.lib.vxrt_set_culling(self._h, 1 if enabled else 0))
+
+    def setOverlap(self, mode):
+        """0 off, 1 on, 2 auto (default): the shade pass starts inside the primary pass's tail (programmatic dependent launch)"""
+        self._check(self.lib.vxrt_set_overlap(self._h, int(mode)))
 
     def setTileOrdering(self, enabled):
         self._check(self.lib.vxrt_set_tile_ordering(self._h, 1 if enabled else 0))

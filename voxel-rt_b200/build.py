@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "vxrt.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "kernels.cuh"), os.path.join(HERE, "csrc", "ray.cuh"),
+DEPS = [SRC, os.path.join(HERE, "csrc", "kernels.cuh"), os.path.join(HERE, "csrc", "ray.cuh"), os.path.join(HERE, "csrc", "trav.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "vxrt.h")]
 LIB = os.path.join(HERE, "libvxrt.so")
 
@@ -102,6 +102,8 @@ VARIANTS = {
     # bench.py's "experiments" object times every entry).  Round 1's late_domain_check is the default now, jump_prefetch
     # (a measured loss) is gone.
     "late_domain_check": ["-DVXRT_LATE_DOMAIN_CHECK"],      # divide before the fast-domain test of a jump's re-base (ray.cuh)
+    "primary_run_min_1": ["-DVXRT_PRIMARY_RUN_MIN=1"],       # primary rays take every run a band word promises (default: >= 8 steps)
+    "primary_run_min_13": ["-DVXRT_PRIMARY_RUN_MIN=13"],
 }
 
 

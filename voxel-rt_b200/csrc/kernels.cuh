@@ -54,6 +54,12 @@ struct Outputs {
     Counters* counters;
     const uint32_t* tile_order;         // optional: launch order of the local tiles (longest first, from the previous frame)
     uint32_t* tile_cost;                // optional: per local tile, SM cycles its block took this frame
+    // overlap of the two passes (programmatic dependent launch): the shade pass starts while the primary pass's last blocks
+    // still run; a shade block waits for ITS tile's flag instead of the kernel boundary
+    uint32_t* tile_ready;               // per local tile: frame_seq of the last primary pass that finished it
+    uint32_t frame_seq;
+    int overlap;
+    int* overlap_err;                   // set when a shade block gave up waiting (bounded spin)
     int32_t* dbg_hit;                   // optional (VXRT_FLAG_DEBUG_OUTPUTS), raster layout
     uint16_t* dbg_steps;
     uint32_t* dbg_occl;
@@ -78,6 +84,9 @@ __global__ void __launch_bounds__(256, 6) primary_kernel(Grid g, const __grid_co
     __shared__ unsigned long long s_fetches;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) s_fetches = 0ull;
+    // overlap: the shade pass (launched with programmatic stream serialization) may be scheduled as soon as every block of this
+    // grid has started, i.e. into the SM capacity this pass's tail leaves idle
+    if (o.overlap) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const long long t_start = clock64();
     // blocks are handed out in launch order: with a tile order from the previous frame the slowest tiles start first,
     // which shortens the kernel's tail (it matters once a GPU renders only 1/4 or 1/8 of the frame)
@@ -138,6 +147,12 @@ __global__ void __launch_bounds__(256, 6) primary_kernel(Grid g, const __grid_co
     }
     if (tid == 0 && s_fetches) atomicAdd(&o.counters->fetches_primary, s_fetches);
     if (tid == 0 && o.tile_cost) o.tile_cost[local_tile] = (uint32_t)min((long long)0xffffffffll, clock64() - t_start);
+    if (o.overlap) {
+        // publish the tile: every thread's hit slots (and the tile's hit count) are written; the barrier orders them before
+        // thread 0's release store, which the tile's shade blocks acquire
+        __syncthreads();
+        if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(o.tile_ready + local_tile), "r"(o.frame_seq) : "memory");
+    }
 }
 
 // cost[n] -> order[n], most expensive first: one-block counting sort on a 128-bucket logarithmic key.  Per-warp
@@ -204,6 +219,22 @@ __global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_cons
     const int unit = o.shade_order ? (int)o.shade_order[blockIdx.x] : (int)blockIdx.x + o.shade_unit_base;
     const int units_per_tile = TILE_PIX / (int)blockDim.x;
     const int tile = unit / units_per_tile, slot0 = (unit % units_per_tile) * (int)blockDim.x, slot = slot0 + tid;
+    if (o.overlap) {
+        // the primary pass may still be running: wait until it has published this tile (bounded: ~2 s, then give up loudly)
+        if (tid == 0) {
+            unsigned v;
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(o.tile_ready + tile) : "memory");
+                if (v == o.frame_seq) break;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 2000000000ull) { *o.overlap_err = 1; break; }
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+    }
     const unsigned count = o.tile_hits[tile];
     if ((unsigned)slot0 >= count) {                                  // sky tile / empty part of a tile: nothing to shade
         if (tid == 0 && o.shade_cost) o.shade_cost[unit] = 0u;

@@ -84,6 +84,11 @@ struct vxrt_ctx {
     int order_shade_threads = 0;        // block size the shade order was recorded with
     unsigned long long order_frame = 0; // whole-frame launches since the ordering was (re)started
     bool use_tile_order = true;
+    int overlap = 2;                    // vxrt_set_overlap: 0 off, 1 on, 2 auto (on when this context renders <= 12,000 tiles) -- the shade
+                                        // pass starts inside the primary pass's tail (programmatic dependent launch + per-tile flags)
+    uint32_t* d_tile_ready = nullptr;   // per local tile: frame_seq of the last primary pass that finished it
+    int* d_overlap_err = nullptr;
+    uint32_t frame_seq = 0;
     bool use_culling = true;
     int l2_prefetch = 2;                // vxrt_set_l2_prefetch: 0 off, 1 on, 2 auto (on when this context renders <= 12,000 tiles)
     int shade_threads = 128;            // threads per shade block (VXRT_SHADE_THREADS: 64 / 128 / 256; 128 measured best)
@@ -143,6 +148,7 @@ static GridView grid_view(const vxrt_ctx* c) {
 static void free_frame_buffers(vxrt_ctx* c) {
     cudaFree(c->d_rgba8); cudaFree(c->d_rgba8_alt); cudaFree(c->d_hitq); cudaFree(c->d_hitpix);
     cudaFree(c->d_tile_cost); cudaFree(c->d_tile_order); cudaFree(c->d_tile_hits); cudaFree(c->d_shade_cost); cudaFree(c->d_shade_order);
+    cudaFree(c->d_tile_ready); c->d_tile_ready = nullptr;
     c->d_tile_cost = nullptr; c->d_tile_order = nullptr; c->d_tile_hits = nullptr; c->d_shade_cost = nullptr; c->d_shade_order = nullptr;
     c->have_tile_order = false; c->have_shade_order = false; c->order_frame = 0;
     c->d_rgba8_alt = nullptr; c->slot_busy[0] = c->slot_busy[1] = false;
@@ -166,6 +172,10 @@ static int alloc_frame_buffers(vxrt_ctx* c) {
     CUDA_TRY(cudaMalloc(&c->d_tile_cost, (size_t)c->map.nlocal * 4));
     CUDA_TRY(cudaMalloc(&c->d_tile_order, (size_t)c->map.nlocal * 4));
     CUDA_TRY(cudaMalloc(&c->d_tile_hits, (size_t)c->map.nlocal * 4));
+    CUDA_TRY(cudaMalloc(&c->d_tile_ready, (size_t)c->map.nlocal * 4));
+    CUDA_TRY(cudaMemsetAsync(c->d_tile_ready, 0, (size_t)c->map.nlocal * 4, c->stream));
+    if (!c->d_overlap_err) { CUDA_TRY(cudaMalloc(&c->d_overlap_err, sizeof(int))); CUDA_TRY(cudaMemsetAsync(c->d_overlap_err, 0, sizeof(int), c->stream)); }
+    c->frame_seq = 0;
     CUDA_TRY(cudaMalloc(&c->d_shade_cost, (size_t)c->map.nlocal * 4 * 4));      // up to 4 units per tile (64-thread blocks)
     CUDA_TRY(cudaMalloc(&c->d_shade_order, (size_t)c->map.nlocal * 4 * 4));
     CUDA_TRY(cudaMemsetAsync(c->d_tile_hits, 0, (size_t)c->map.nlocal * 4, c->stream));
@@ -378,6 +388,7 @@ extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     vxrt_init_local_lights(c);
     if (const char* e = getenv("VXRT_L2_PREFETCH")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->l2_prefetch = v; }
     if (const char* e = getenv("VXRT_TRAVERSAL")) c->trav_enabled = atoi(e) != 0;
+    if (const char* e = getenv("VXRT_OVERLAP")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->overlap = v; }
     if (const char* e = getenv("VXRT_SHADE_THREADS")) {
         const int v = atoi(e);
         if (v == 64 || v == 128 || v == 256) c->shade_threads = v;
@@ -394,6 +405,7 @@ extern "C" void vxrt_destroy(vxrt_ctx* c) {
     free_frame_buffers(c);
     if (c->p2p_base) { if (c->p2p_owner) cudaFree(c->p2p_base); else if (!c->p2p_attached) cudaIpcCloseMemHandle(c->p2p_base); }
     cudaFree(c->d_p2p_err);
+    cudaFree(c->d_overlap_err);
     cudaFree(c->d_yrange);
     cudaFree(c->d_vox); cudaFree(c->d_trav); cudaFree(c->d_trav_bad); cudaFree(c->d_counters); cudaFree(c->d_stage); cudaFree(c->d_first);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -932,39 +944,66 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         o.shade_unit_base = tile0 * upt;
         o.dbg_hit = c->d_dbg_hit; o.dbg_steps = c->d_dbg_steps; o.dbg_occl = c->d_dbg_occl; o.dbg_cast = c->d_dbg_cast;
         const dim3 grid(ntile), block(256);
-        // kernel variants: <iteration counters, grid type (reference extents as compile-time constants / runtime extents), traversal grid>
-#define VXRT_LAUNCH(KERNEL, COUNT, GRID, BLOCK)                                                                              \
+        // kernel variants: <iteration counters, grid type (reference extents as compile-time constants / runtime extents), traversal grid>;
+        // PDL: launched with programmatic stream serialization (the shade pass of an overlapped frame)
+#define VXRT_LAUNCH1(KERNEL, GRID, BLOCK, PDL, GV)                                                                            \
+        do {                                                                                                                  \
+            cudaLaunchConfig_t lc;                                                                                            \
+            memset(&lc, 0, sizeof lc);                                                                                        \
+            lc.gridDim = GRID; lc.blockDim = BLOCK; lc.dynamicSmemBytes = 0; lc.stream = c->stream;                            \
+            cudaLaunchAttribute la[1];                                                                                        \
+            la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                    \
+            la[0].val.programmaticStreamSerializationAllowed = 1;                                                             \
+            lc.attrs = la; lc.numAttrs = (PDL) ? 1 : 0;                                                                       \
+            CUDA_TRY(cudaLaunchKernelEx(&lc, KERNEL, GV, fp, m, o));                                                          \
+        } while (0)
+#define VXRT_LAUNCH(KERNEL, COUNT, GRID, BLOCK, PDL)                                                                          \
         do {                                                                                                                  \
             if (ref_dims) {                                                                                                   \
-                if (COUNT) { if (trav) KERNEL<true, GridViewRef, true><<<GRID, BLOCK, 0, c->stream>>>(gr, fp, m, o);          \
-                             else KERNEL<true, GridViewRef, false><<<GRID, BLOCK, 0, c->stream>>>(gr, fp, m, o); }            \
-                else       { if (trav) KERNEL<false, GridViewRef, true><<<GRID, BLOCK, 0, c->stream>>>(gr, fp, m, o);         \
-                             else KERNEL<false, GridViewRef, false><<<GRID, BLOCK, 0, c->stream>>>(gr, fp, m, o); }           \
+                if (COUNT) { if (trav) VXRT_LAUNCH1((KERNEL<true, GridViewRef, true>), GRID, BLOCK, PDL, gr);                 \
+                             else VXRT_LAUNCH1((KERNEL<true, GridViewRef, false>), GRID, BLOCK, PDL, gr); }                   \
+                else       { if (trav) VXRT_LAUNCH1((KERNEL<false, GridViewRef, true>), GRID, BLOCK, PDL, gr);                \
+                             else VXRT_LAUNCH1((KERNEL<false, GridViewRef, false>), GRID, BLOCK, PDL, gr); }                  \
             } else {                                                                                                          \
-                if (COUNT) { if (trav) KERNEL<true, GridView, true><<<GRID, BLOCK, 0, c->stream>>>(g, fp, m, o);              \
-                             else KERNEL<true, GridView, false><<<GRID, BLOCK, 0, c->stream>>>(g, fp, m, o); }                \
-                else       { if (trav) KERNEL<false, GridView, true><<<GRID, BLOCK, 0, c->stream>>>(g, fp, m, o);             \
-                             else KERNEL<false, GridView, false><<<GRID, BLOCK, 0, c->stream>>>(g, fp, m, o); }               \
+                if (COUNT) { if (trav) VXRT_LAUNCH1((KERNEL<true, GridView, true>), GRID, BLOCK, PDL, g);                     \
+                             else VXRT_LAUNCH1((KERNEL<true, GridView, false>), GRID, BLOCK, PDL, g); }                       \
+                else       { if (trav) VXRT_LAUNCH1((KERNEL<false, GridView, true>), GRID, BLOCK, PDL, g);                    \
+                             else VXRT_LAUNCH1((KERNEL<false, GridView, false>), GRID, BLOCK, PDL, g); }                      \
             }                                                                                                                 \
         } while (0)
-        VXRT_LAUNCH(primary_kernel, count_primary, grid, block);
+        // overlap (whole-frame launches of the lit view only): nothing may be queued between the two passes, so the event that
+        // separates their times and the refresh of the primary launch order move behind the shade pass
+        const bool overlap = nbands == 1 && c->frame.view_depth_field != 1 &&
+                             (c->overlap == 1 || (c->overlap == 2 && c->map.nlocal <= 12000));
+        o.overlap = overlap ? 1 : 0;
+        o.tile_ready = c->d_tile_ready; o.overlap_err = c->d_overlap_err;
+        o.frame_seq = ++c->frame_seq;
+        VXRT_LAUNCH(primary_kernel, count_primary, grid, block, false);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
-        if (nbands == 1) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        if (nbands == 1 && !overlap) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
         // the launch orders are refreshed on the first two frames and then every 8th (block times are temporally
         // coherent; the one-block sort costs ~30 us at 4K)
         const bool refresh_order = c->order_frame < 2 || (c->order_frame % 8) == 0;
-        if (o.tile_cost && c->map.nlocal >= 64 && refresh_order) {
-            tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_tile_cost, c->d_tile_order, c->map.nlocal);
-            CUDA_TRY(cudaGetLastError());
-            c->launches++;
-            c->have_tile_order = true;
-        }
+        auto refresh_tile_order = [&]() -> int {
+            if (o.tile_cost && c->map.nlocal >= 64 && refresh_order) {
+                tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_tile_cost, c->d_tile_order, c->map.nlocal);
+                CUDA_TRY(cudaGetLastError());
+                c->launches++;
+                c->have_tile_order = true;
+            }
+            return VXRT_OK;
+        };
+        if (!overlap) { const int rc = refresh_tile_order(); if (rc != VXRT_OK) return rc; }
         if (c->frame.view_depth_field != 1) {
             const dim3 sblock(c->shade_threads), sgrid((unsigned)(((size_t)ntile * TILE_PIX + c->shade_threads - 1) / c->shade_threads));
-            VXRT_LAUNCH(shade_kernel, count, sgrid, sblock);
+            VXRT_LAUNCH(shade_kernel, count, sgrid, sblock, overlap);
             CUDA_TRY(cudaGetLastError());
             c->launches++;
+            if (overlap) {
+                CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));      // (the passes overlap: ms_primary then reads as the whole frame, ms_shadow as 0)
+                const int rc = refresh_tile_order(); if (rc != VXRT_OK) return rc;
+            }
             if (o.shade_cost && c->map.nlocal >= 64 && refresh_order) {
                 tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_shade_cost, c->d_shade_order, c->map.nlocal * upt);
                 CUDA_TRY(cudaGetLastError());
@@ -1043,6 +1082,13 @@ extern "C" int vxrt_download_traversal(vxrt_ctx* c, int32_t* out, size_t count) 
     if (!out || count != c->nvox) return fail(VXRT_ERR_INVALID, "download_traversal: count must equal grid_w*grid_h*grid_d");
     CUDA_TRY(cudaMemcpyAsync(out, c->d_trav, count * 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_set_overlap(vxrt_ctx* c, int mode) {
+    if (!c) return fail(VXRT_ERR_INVALID, "null context");
+    if (mode < 0 || mode > 2) return fail(VXRT_ERR_INVALID, "set_overlap: 0 off, 1 on, 2 auto");
+    c->overlap = mode;
     return VXRT_OK;
 }
 
