@@ -913,7 +913,8 @@ def reference_frame_runner(workload, stride, level=None):
         def run(reps):
             r = subprocess.run([cli, gpath, fpath, str(W), str(H), str(cores), str(reps), str(stride)], capture_output=True, text=True, check=True)
             return [float(x) for x in r.stdout.split()]
-        return run, rays, "reference", cores, sample + "; unmodified fshader.glsl compiled for the CPU via the reference's GLM, %d forked workers" % cores
+        return run, rays, "reference", cores, sample + ("; unmodified fshader.glsl compiled for the CPU via the reference's GLM (g++ -O2 -ffp-contract=off, no -march=native: the binary is "
+                                                     "built in the build container and travels), %d persistent forked workers, timed between barriers" % cores)
 
     def run(reps):
         ts = []

@@ -178,11 +178,14 @@ int vxrt_set_culling(vxrt_ctx* ctx, int enabled);
    cell as the reference layout; a -1 cell (empty, no depth-field jump) carries, per travel quadrant, how many further cells of
    its y layer (and of the layer above) are -1 cells inside the grid, and castRay takes those steps without index arithmetic,
    range test or load -- exact by adjacency: a step moves one cell along one axis whatever the float state says.  It is kept
-   coherent by every upload / edit entry point (a rebuild over the cells whose words can change).  enabled (default): rays read
-   it; disabled: rays read the reference-layout grid with the plain kernels.  Same pixels either way.  vxrt_traversal_active:
-   1 if the next frame reads the traversal grid (0 also when the grid holds a value that cannot be encoded: a negative int
-   with bit 30 clear other than through -1, which the reference never produces).  vxrt_download_traversal: the words, for tests. */
-int vxrt_set_traversal(vxrt_ctx* ctx, int enabled);
+   coherent by every upload / edit entry point (a rebuild over the cells whose words can change).  mode 0: rays read the
+   reference-layout grid with the plain kernels; 1: both passes read the traversal grid; 2 (default, auto): the shade pass
+   always, the primary pass when this context renders <= 12,000 tiles (a 1080p frame, a share of a 4K frame: there its runs
+   shorten the critical path; on a whole 4K frame they cost the primary pass throughput).  Same pixels in every mode.
+   vxrt_traversal_active: 1 if the next frame reads the traversal grid (0 also when the grid holds a value that cannot be
+   encoded: a negative int with bit 30 clear other than through -1, which the reference never produces).
+   vxrt_download_traversal: the words, for tests. */
+int vxrt_set_traversal(vxrt_ctx* ctx, int mode);
 int vxrt_traversal_active(vxrt_ctx* ctx);
 int vxrt_download_traversal(vxrt_ctx* ctx, int32_t* out, size_t count);
 /* enabled (default): the primary pass records how long each tile's block took and the next frame launches the
@@ -225,6 +228,10 @@ int vxrt_read_rgba8(vxrt_ctx* ctx, uint8_t* out);            /* width*height*4 (
    occluded, bit(1+i) = local light i occluded; cast_mask: same bits, "ray was cast" */
 int vxrt_read_debug(vxrt_ctx* ctx, int32_t* hit_index, uint16_t* steps, uint32_t* occl_mask, uint32_t* cast_mask);
 int vxrt_get_stats(vxrt_ctx* ctx, vxrt_stats* out);
+/* diagnostics: SM cycles each local tile's primary block and each shade unit's block took in the last whole-frame launch (what
+   the slowest-first launch orders are made from).  primary: vxrt_local_tiles() entries; shade: shade_count = local tiles x
+   (256 / threads per shade block, 2 by default) entries; either may be NULL */
+int vxrt_read_block_costs(vxrt_ctx* ctx, uint32_t* primary, uint32_t* shade, size_t shade_count);
 /* known-answer hook: castRay(start, dir, dist) fshader.glsl:59-129 for n independent rays (host arrays:
    starts/dirs n*3 floats, dists n ints); ret[n] = return value, out7[n*7] = hitPos[3] hitNormal[3] stepCount */
 int vxrt_cast_rays(vxrt_ctx* ctx, int32_t n, const float* starts, const float* dirs, const int32_t* dists,

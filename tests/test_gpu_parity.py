@@ -203,6 +203,11 @@ def test_pipelined_frame_submission(vx, oracle, default_level):
         r.waitFrames()
         for k, name in enumerate(names):
             assert np.array_equal(bufs[k], oracle.render(default_level, gc.DIMS, gc.frame_cases(W, H)[name], W, H)["rgba8"]), (k, name)
+        # 7 submits alternate between two device buffers: read_rgba8 must return the LAST frame, whichever buffer holds it
+        assert np.array_equal(r.readPixels(), bufs[6])
+        r.submitFrameHost(to_vx_frame(vx, gc.frame_cases(W, H)["low_sun"]), bufs[0])
+        r.waitFrames()
+        assert np.array_equal(r.readPixels(), bufs[5]) and np.array_equal(bufs[0], bufs[5])
         with pytest.raises(vx.VxrtError, match="page-locked"):
             r.submitFrameHost(to_vx_frame(vx, gc.frame_cases(W, H)["C1"]), np.empty((H, W, 4), np.uint8))
         # synchronous calls still work afterwards
@@ -521,6 +526,11 @@ def test_peer_memory_frame_target_protocol_on_one_gpu(vx, oracle, default_level)
         for r in ctxs:
             r.updateGeometry(default_level)
         ctxs[0].p2pExport()
+        # an importer whose frame extents or world size differ from the owner's allocation would store out of bounds: refused
+        for bad in (dict(width=W + 32, height=H, rank=1, world=world), dict(width=W, height=H, rank=1, world=world + 1)):
+            with vx.Renderer(grid=(16, 16, 16), **bad) as other:
+                with pytest.raises(vx.VxrtError, match="owner's frame"):
+                    other.p2pAttach(ctxs[0])
         for r in ctxs[1:]:
             r.p2pAttach(ctxs[0])
         names = ["C3ii_pitched", "C2", "C3i", "sparse_lights", "C1"]          # 5 frames > 2 buffers: exercises the back-pressure

@@ -93,6 +93,7 @@ _SIGNATURES = {
     "vxrt_read_rgba8": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vxrt_read_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vxrt_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "vxrt_read_block_costs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "vxrt_cast_rays": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vxrt_selftest_division": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "vxrt_write_ppm": (C.c_int, [C.c_void_p, C.c_char_p]),
@@ -285,9 +286,10 @@ class Renderer:
         assert p.shape[0] == v.size
         self._check(self.lib.vxrt_place_voxels(self._h, v.size, _vp(p), _vp(v)))
 
-    def setTraversal(self, enabled):
-        """rays read the traversal grid (default) or the reference-layout grid with the plain kernels; same pixels"""
-        self._check(self.lib.vxrt_set_traversal(self._h, 1 if enabled else 0))
+    def setTraversal(self, mode):
+        """0 / False: rays read the reference-layout grid with the plain kernels; 1 / True: both passes read the traversal grid;
+        2 (default): the shade pass always, the primary pass for small shares.  Same pixels."""
+        self._check(self.lib.vxrt_set_traversal(self._h, int(mode)))
 
     def traversalActive(self):
         return bool(self.lib.vxrt_traversal_active(self._h))
@@ -452,6 +454,14 @@ class Renderer:
         s = Stats()
         self._check(self.lib.vxrt_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def blockCosts(self, shade_units_per_tile=2):
+        """(primary, shade): SM cycles of each local tile's primary block / each shade unit's block in the last whole-frame launch"""
+        n = int(self.lib.vxrt_local_tiles(self._h))
+        p = np.zeros(n, np.uint32)
+        s = np.zeros(n * shade_units_per_tile, np.uint32)
+        self._check(self.lib.vxrt_read_block_costs(self._h, _vp(p), _vp(s), s.size))
+        return p, s
 
     def castRays(self, starts, dirs, dists):
         """castRay known-answer hook (fshader.glsl:59-129): returns (ret[n], out7[n,7])."""

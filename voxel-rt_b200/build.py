@@ -101,9 +101,7 @@ VARIANTS = {
     # default library stays exactly what was validated (VXRT_LIB=... pytest -m gpu runs the whole parity suite on one;
     # bench.py's "experiments" object times every entry).  Round 1's late_domain_check is the default now, jump_prefetch
     # (a measured loss) is gone.
-    "late_domain_check": ["-DVXRT_LATE_DOMAIN_CHECK"],      # divide before the fast-domain test of a jump's re-base (ray.cuh)
-    "primary_run_min_1": ["-DVXRT_PRIMARY_RUN_MIN=1"],       # primary rays take every run a band word promises (default: >= 8 steps)
-    "primary_run_min_13": ["-DVXRT_PRIMARY_RUN_MIN=13"],
+    "early_domain_check": ["-DVXRT_EARLY_DOMAIN_CHECK"],    # test the fast domain of a jump's re-base before dividing (ray.cuh; round 1's order)
 }
 
 

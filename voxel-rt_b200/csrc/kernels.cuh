@@ -512,7 +512,8 @@ __global__ void division_selftest_kernel(unsigned long long n, unsigned long lon
 // hang the GPU: on time-out *err is set and the kernel returns.
 struct P2PShared {
     unsigned long long consumed;        // frames the owner has finished reading (written by the owner)
-    unsigned long long pad0[15];
+    unsigned long long width, height, world;   // the owner's frame extents and world size (importers must match them)
+    unsigned long long pad0[12];
     unsigned long long done[16 * 16];   // done[16*r] = frames rank r has completely written (stride 128 B)
 };
 

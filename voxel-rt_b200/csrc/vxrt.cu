@@ -60,7 +60,8 @@ struct vxrt_ctx {
     int32_t* d_trav = nullptr;
     unsigned long long* d_trav_bad = nullptr;
     unsigned long long trav_bad = 0;    // cells whose value cannot be encoded (then the rays read d_vox with the plain kernels)
-    bool trav_enabled = true;           // vxrt_set_traversal
+    int trav_mode = 2;                  // vxrt_set_traversal: 0 off, 1 both passes, 2 auto (shade pass always; primary pass when this context
+                                        // renders <= 12,000 tiles: there its runs shorten the critical path, on a whole 4K frame they cost throughput)
     size_t nvox = 0;
     bool grid_loaded = false;
     int yrange[2] = {INT_MAX, INT_MIN};  // rows holding solid voxels (never shrinks on destruction: conservative)
@@ -105,6 +106,7 @@ struct vxrt_ctx {
     uint8_t* h_frame = nullptr;         // pinned read-back buffer
     size_t h_frame_cap = 0;
     bool rendered = false;
+    const uint32_t* d_last_frame = nullptr;     // the device buffer the last frame was rendered into (vxrt_read_rgba8 / vxrt_write_ppm)
     int bands_used = 1;
     // peer-memory frame target (vxrt_p2p_*)
     bool p2p = false, p2p_owner = false, p2p_attached = false;
@@ -130,7 +132,8 @@ static TileMap make_map(int width, int height, int rank, int world) {
     return m;
 }
 
-static bool use_trav(const vxrt_ctx* c) { return c->trav_enabled && c->trav_bad == 0 && c->d_trav != nullptr; }
+static bool use_trav(const vxrt_ctx* c) { return c->trav_mode != 0 && c->trav_bad == 0 && c->d_trav != nullptr; }
+static bool use_trav_primary(const vxrt_ctx* c) { return use_trav(c) && (c->trav_mode == 1 || c->map.nlocal <= 12000); }
 
 static GridView grid_view(const vxrt_ctx* c) {
     GridView g;
@@ -149,6 +152,7 @@ static void free_frame_buffers(vxrt_ctx* c) {
     cudaFree(c->d_rgba8); cudaFree(c->d_rgba8_alt); cudaFree(c->d_hitq); cudaFree(c->d_hitpix);
     cudaFree(c->d_tile_cost); cudaFree(c->d_tile_order); cudaFree(c->d_tile_hits); cudaFree(c->d_shade_cost); cudaFree(c->d_shade_order);
     cudaFree(c->d_tile_ready); c->d_tile_ready = nullptr;
+    c->d_last_frame = nullptr;
     c->d_tile_cost = nullptr; c->d_tile_order = nullptr; c->d_tile_hits = nullptr; c->d_shade_cost = nullptr; c->d_shade_order = nullptr;
     c->have_tile_order = false; c->have_shade_order = false; c->order_frame = 0;
     c->d_rgba8_alt = nullptr; c->slot_busy[0] = c->slot_busy[1] = false;
@@ -387,7 +391,7 @@ extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     for (int i = 0; i < 4; i++) c->frame.rotate[5 * i] = 1.0f;
     vxrt_init_local_lights(c);
     if (const char* e = getenv("VXRT_L2_PREFETCH")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->l2_prefetch = v; }
-    if (const char* e = getenv("VXRT_TRAVERSAL")) c->trav_enabled = atoi(e) != 0;
+    if (const char* e = getenv("VXRT_TRAVERSAL")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->trav_mode = v; }
     if (const char* e = getenv("VXRT_OVERLAP")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->overlap = v; }
     if (const char* e = getenv("VXRT_SHADE_THREADS")) {
         const int v = atoi(e);
@@ -882,8 +886,12 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
     const bool counted_full = c->stats_mode == 1 || (c->stats_mode == 0 && c->d_dbg_hit != nullptr);
     const bool count_primary = count || c->frame.view_depth_field == 1;
     const bool ref_dims = (g.w == GridViewRef::w && g.h == GridViewRef::h && g.d == GridViewRef::d);
-    const bool trav = use_trav(c);
     GridViewRef gr; gr.vox = g.vox; gr.ymin = g.ymin; gr.ymax = g.ymax;
+    // the two passes may read different copies of the grid (vxrt_set_traversal, auto): the traversal grid or the reference-layout one
+    const bool trav_shade = use_trav(c), trav_primary = use_trav_primary(c);
+    GridView g_plain = g, g_trav = g;
+    GridViewRef gr_plain = gr, gr_trav = gr;
+    g_plain.vox = c->d_vox; gr_plain.vox = c->d_vox; g_trav.vox = c->d_trav; gr_trav.vox = c->d_trav;
     // bands: whole tile rows when this context owns the whole frame (raster rows stay contiguous), else tile ranges
     const int units = (c->cfg.world == 1) ? c->map.ty : c->map.nlocal;
     const int tiles_per_unit = (c->cfg.world == 1) ? c->map.tx : 1;
@@ -908,7 +916,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         const int slab_ints = c->cfg.grid_w * c->cfg.grid_h;
         const int lines_per_slab = (c->cfg.grid_w * ytop + 31) / 32;
         const long long nlines = (long long)lines_per_slab * c->cfg.grid_d;
-        l2_prefetch_kernel<<<148 * 8, 256, 0, c->stream>>>(g.vox, lines_per_slab, slab_ints, nlines, c->d_yrange ? c->d_yrange + 2 : nullptr);
+        l2_prefetch_kernel<<<148 * 8, 256, 0, c->stream>>>(trav_primary ? c->d_trav : c->d_vox, lines_per_slab, slab_ints, nlines, c->d_yrange ? c->d_yrange + 2 : nullptr);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
     }
@@ -957,18 +965,18 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
             lc.attrs = la; lc.numAttrs = (PDL) ? 1 : 0;                                                                       \
             CUDA_TRY(cudaLaunchKernelEx(&lc, KERNEL, GV, fp, m, o));                                                          \
         } while (0)
-#define VXRT_LAUNCH(KERNEL, COUNT, GRID, BLOCK, PDL)                                                                          \
+#define VXRT_LAUNCH(KERNEL, COUNT, TRAV, GRID, BLOCK, PDL)                                                                    \
         do {                                                                                                                  \
             if (ref_dims) {                                                                                                   \
-                if (COUNT) { if (trav) VXRT_LAUNCH1((KERNEL<true, GridViewRef, true>), GRID, BLOCK, PDL, gr);                 \
-                             else VXRT_LAUNCH1((KERNEL<true, GridViewRef, false>), GRID, BLOCK, PDL, gr); }                   \
-                else       { if (trav) VXRT_LAUNCH1((KERNEL<false, GridViewRef, true>), GRID, BLOCK, PDL, gr);                \
-                             else VXRT_LAUNCH1((KERNEL<false, GridViewRef, false>), GRID, BLOCK, PDL, gr); }                  \
+                if (COUNT) { if (TRAV) VXRT_LAUNCH1((KERNEL<true, GridViewRef, true>), GRID, BLOCK, PDL, gr_trav);            \
+                             else VXRT_LAUNCH1((KERNEL<true, GridViewRef, false>), GRID, BLOCK, PDL, gr_plain); }             \
+                else       { if (TRAV) VXRT_LAUNCH1((KERNEL<false, GridViewRef, true>), GRID, BLOCK, PDL, gr_trav);           \
+                             else VXRT_LAUNCH1((KERNEL<false, GridViewRef, false>), GRID, BLOCK, PDL, gr_plain); }            \
             } else {                                                                                                          \
-                if (COUNT) { if (trav) VXRT_LAUNCH1((KERNEL<true, GridView, true>), GRID, BLOCK, PDL, g);                     \
-                             else VXRT_LAUNCH1((KERNEL<true, GridView, false>), GRID, BLOCK, PDL, g); }                       \
-                else       { if (trav) VXRT_LAUNCH1((KERNEL<false, GridView, true>), GRID, BLOCK, PDL, g);                    \
-                             else VXRT_LAUNCH1((KERNEL<false, GridView, false>), GRID, BLOCK, PDL, g); }                      \
+                if (COUNT) { if (TRAV) VXRT_LAUNCH1((KERNEL<true, GridView, true>), GRID, BLOCK, PDL, g_trav);                \
+                             else VXRT_LAUNCH1((KERNEL<true, GridView, false>), GRID, BLOCK, PDL, g_plain); }                 \
+                else       { if (TRAV) VXRT_LAUNCH1((KERNEL<false, GridView, true>), GRID, BLOCK, PDL, g_trav);               \
+                             else VXRT_LAUNCH1((KERNEL<false, GridView, false>), GRID, BLOCK, PDL, g_plain); }                \
             }                                                                                                                 \
         } while (0)
         // overlap (whole-frame launches of the lit view only): nothing may be queued between the two passes, so the event that
@@ -978,7 +986,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         o.overlap = overlap ? 1 : 0;
         o.tile_ready = c->d_tile_ready; o.overlap_err = c->d_overlap_err;
         o.frame_seq = ++c->frame_seq;
-        VXRT_LAUNCH(primary_kernel, count_primary, grid, block, false);
+        VXRT_LAUNCH(primary_kernel, count_primary, trav_primary, grid, block, false);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
         if (nbands == 1 && !overlap) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -997,7 +1005,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         if (!overlap) { const int rc = refresh_tile_order(); if (rc != VXRT_OK) return rc; }
         if (c->frame.view_depth_field != 1) {
             const dim3 sblock(c->shade_threads), sgrid((unsigned)(((size_t)ntile * TILE_PIX + c->shade_threads - 1) / c->shade_threads));
-            VXRT_LAUNCH(shade_kernel, count, sgrid, sblock, overlap);
+            VXRT_LAUNCH(shade_kernel, count, trav_shade, sgrid, sblock, overlap);
             CUDA_TRY(cudaGetLastError());
             c->launches++;
             if (overlap) {
@@ -1039,6 +1047,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
     }
     c->rendered = true;
+    c->d_last_frame = (p2p_frame || raster_out) ? nullptr : dev_out;    // (frames stored into a peer / host frame are not kept here)
     return VXRT_OK;
 }
 
@@ -1067,9 +1076,10 @@ extern "C" int vxrt_set_culling(vxrt_ctx* c, int enabled) {
     return VXRT_OK;
 }
 
-extern "C" int vxrt_set_traversal(vxrt_ctx* c, int enabled) {
+extern "C" int vxrt_set_traversal(vxrt_ctx* c, int mode) {
     if (!c) return fail(VXRT_ERR_INVALID, "null context");
-    c->trav_enabled = enabled != 0;
+    if (mode < 0 || mode > 2) return fail(VXRT_ERR_INVALID, "set_traversal: 0 off, 1 both passes, 2 auto");
+    c->trav_mode = mode;
     return VXRT_OK;
 }
 
@@ -1176,7 +1186,9 @@ extern "C" int vxrt_read_rgba8(vxrt_ctx* c, uint8_t* out) {
     CHECK_CTX(c);
     if (!out) return fail(VXRT_ERR_INVALID, "read_rgba8: null output");
     if (!c->rendered) return fail(VXRT_ERR_STATE, "read_rgba8 before render");
-    CUDA_TRY(cudaMemcpyAsync(out, c->d_rgba8, c->out_pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (!c->d_last_frame) return fail(VXRT_ERR_STATE, "read_rgba8: the last frame was stored into a peer-memory / host frame, not into this context's buffer");
+    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));       // a pipelined read-back of that buffer may still be in flight
+    CUDA_TRY(cudaMemcpyAsync(out, c->d_last_frame, c->out_pixels * 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return VXRT_OK;
 }
@@ -1228,6 +1240,20 @@ extern "C" int vxrt_get_stats(vxrt_ctx* c, vxrt_stats* out) {
     CUDA_TRY(cudaEventElapsedTime(&out->ms_shadow, c->ev[1], c->ev[2]));
     CUDA_TRY(cudaEventElapsedTime(&out->ms_total, c->ev[0], c->ev[2]));
     out->kernel_launches = c->launches;
+    return VXRT_OK;
+}
+
+// diagnostics: SM cycles each local tile's primary block / each shade unit's block took in the last whole-frame launch (the
+// figures the slowest-first launch orders are made from); either pointer may be null.  Sizes: vxrt_local_tiles() and
+// vxrt_local_tiles() * (256 / shade threads per block) entries
+extern "C" int vxrt_read_block_costs(vxrt_ctx* c, uint32_t* primary, uint32_t* shade, size_t shade_count) {
+    CHECK_CTX(c);
+    if (!c->rendered) return fail(VXRT_ERR_STATE, "read_block_costs before render");
+    const size_t upt = (size_t)(TILE_PIX / c->shade_threads);
+    if (shade && shade_count != (size_t)c->map.nlocal * upt) return fail(VXRT_ERR_INVALID, "read_block_costs: shade_count must be local tiles * units per tile");
+    if (primary) CUDA_TRY(cudaMemcpyAsync(primary, c->d_tile_cost, (size_t)c->map.nlocal * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (shade) CUDA_TRY(cudaMemcpyAsync(shade, c->d_shade_cost, shade_count * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     return VXRT_OK;
 }
 
@@ -1315,12 +1341,28 @@ extern "C" int vxrt_p2p_export(vxrt_ctx* c, uint8_t handle[64]) {
     const size_t total = sizeof(P2PShared) + 2 * c->p2p_frame_bytes;
     CUDA_TRY(cudaMalloc(&c->p2p_base, total));
     CUDA_TRY(cudaMemset(c->p2p_base, 0, total));
+    {   // header: what an importer's context must look like
+        const unsigned long long hdr[3] = {(unsigned long long)c->cfg.width, (unsigned long long)c->cfg.height, (unsigned long long)c->cfg.world};
+        CUDA_TRY(cudaMemcpy(c->p2p_base + offsetof(P2PShared, width), hdr, sizeof hdr, cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(cudaMalloc(&c->d_p2p_err, sizeof(int)));
     CUDA_TRY(cudaMemset(c->d_p2p_err, 0, sizeof(int)));
     cudaIpcMemHandle_t h;
     CUDA_TRY(cudaIpcGetMemHandle(&h, c->p2p_base));
     memcpy(handle, &h, 64);
     c->p2p = true; c->p2p_owner = true; c->p2p_seq = 0;
+    return VXRT_OK;
+}
+
+// an importer stores into the owner's frame with ITS OWN extents and rank: both must be what the owner allocated for
+static int p2p_check_header(vxrt_ctx* c, const void* base) {
+    if (c->cfg.world > 16 || c->cfg.rank >= 16) return fail(VXRT_ERR_INVALID, "peer-memory target supports up to 16 ranks");
+    unsigned long long hdr[3] = {0, 0, 0};
+    CUDA_TRY(cudaMemcpy(hdr, (const uint8_t*)base + offsetof(P2PShared, width), sizeof hdr, cudaMemcpyDeviceToHost));
+    if (hdr[0] != (unsigned long long)c->cfg.width || hdr[1] != (unsigned long long)c->cfg.height || hdr[2] != (unsigned long long)c->cfg.world)
+        return fail(VXRT_ERR_INVALID, "peer-memory target: the owner's frame is " + std::to_string(hdr[0]) + "x" + std::to_string(hdr[1]) + " for " +
+                    std::to_string(hdr[2]) + " ranks, this context renders " + std::to_string(c->cfg.width) + "x" + std::to_string(c->cfg.height) +
+                    " as one of " + std::to_string(c->cfg.world));
     return VXRT_OK;
 }
 
@@ -1332,6 +1374,7 @@ extern "C" int vxrt_p2p_import(vxrt_ctx* c, const uint8_t handle[64]) {
     memcpy(&h, handle, 64);
     void* p = nullptr;
     CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    { const int rc = p2p_check_header(c, p); if (rc != VXRT_OK) { cudaIpcCloseMemHandle(p); return rc; } }
     c->p2p_base = (uint8_t*)p;
     c->p2p_frame_bytes = (size_t)c->cfg.width * c->cfg.height * 4;
     CUDA_TRY(cudaMalloc(&c->d_p2p_err, sizeof(int)));
@@ -1345,6 +1388,7 @@ extern "C" int vxrt_p2p_attach(vxrt_ctx* c, void* owner_base) {
     CHECK_CTX(c);
     if (!owner_base) return fail(VXRT_ERR_INVALID, "p2p_attach: null base");
     if (c->p2p) return fail(VXRT_ERR_STATE, "peer-memory target already set");
+    { const int rc = p2p_check_header(c, owner_base); if (rc != VXRT_OK) return rc; }
     c->p2p_base = (uint8_t*)owner_base;
     c->p2p_frame_bytes = (size_t)c->cfg.width * c->cfg.height * 4;
     CUDA_TRY(cudaMalloc(&c->d_p2p_err, sizeof(int)));

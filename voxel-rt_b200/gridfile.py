@@ -1,7 +1,9 @@
 """VXRTGRD1 grid files on the host (the same format vxrt_save_grid / vxrt_load_grid stream to and from the device,
 include/vxrt.h): 64-byte little-endian header + int32 voxels in the reference's order (x + w*y + w*h*z).  The
 reference has no on-disk format (its level exists only as level.cpp's generator); this one exists so that benchmark
-inputs and edited levels can be reproduced exactly.  Pure numpy, no device."""
+inputs and edited levels can be reproduced exactly.  No device is needed; the payload fingerprint is
+computed by the FNV helper that libvxrt.so exports (host code; importing it loads -- and, if its sources are newer, builds -- the
+library, which itself needs no GPU to load)."""
 import struct
 
 import numpy as np
