@@ -297,16 +297,17 @@ def run_b200(args):
     t_wall = time.perf_counter() - t_wall0
     kern_ms_source = "CUDA events inside vxrt_render, frames of the timed region"
     if frame.view_depth_field != 1 and max(kern_ms["shade"]) == 0.0:
-        # the two passes overlap in this configuration (vxrt_set_overlap, auto): their separate durations come from the same frames
-        # rendered once more with the overlap switched off
+        # the two passes are ONE kernel in this configuration (vxrt_set_fusion, auto): their separate durations come from the same
+        # frames rendered once more as two kernels
         kern_ms = {"primary": [], "shade": []}
-        ren.setOverlap(0)
-        for k in range(2 + min(args.steps, 10)):
+        ren.setFusion(0)
+        for k in range(4 + min(args.steps, 10)):
             flush_l2(); step_device(); ren.sync()
-            if k >= 2:
+            if k >= 4:
                 s = ren.stats(); kern_ms["primary"].append(s["ms_primary"]); kern_ms["shade"].append(s["ms_shadow"])
-        ren.setOverlap(2)
-        kern_ms_source = "CUDA events inside vxrt_render, the timed region's frames rendered again with the overlap of the two passes off (the timed region itself overlaps them)"
+        ren.setFusion(2)
+        kern_ms_source = ("CUDA events inside vxrt_render, the timed region's frames rendered again as two kernels (the timed region runs this share "
+                          "of the frame as ONE fused kernel, vxrt_set_fusion auto: primary rays + lighting per tile)")
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))

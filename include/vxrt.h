@@ -191,13 +191,21 @@ int vxrt_download_traversal(vxrt_ctx* ctx, int32_t* out, size_t count);
 /* enabled (default): the primary pass records how long each tile's block took and the next frame launches the
    slowest tiles first (shorter kernel tail; it matters when a GPU renders only a fraction of the frame).  Same pixels. */
 int vxrt_set_tile_ordering(vxrt_ctx* ctx, int enabled);
-/* Overlap of the two passes of a frame: 0 off, 1 on, 2 auto (default: on when this context renders <= 12,000 tiles, i.e. a
-   1080p frame or a share of a 4K frame -- where the serial tail of the primary pass's longest rays, not throughput, sets the
-   time).  On: the shade kernel is launched with programmatic stream serialization and the primary kernel releases it at once
+/* Overlap of the two passes of a two-kernel frame: 0 off (default), 1 on, 2 auto (on when this context renders <= 12,000
+   tiles).  Superseded by vxrt_set_fusion for small shares (measured on 1/8 of a 4K frame: 0.190 ms separate, 0.181 ms
+   overlapped); kept as a switch.  On: the shade kernel is launched with programmatic stream serialization and the primary kernel releases it at once
    (griddepcontrol.launch_dependents), so shade blocks are scheduled into the SM capacity the primary pass's tail leaves idle;
    a shade block waits for ITS tile's ready flag (release / acquire, bounded spin) instead of the kernel boundary.  Same
    pixels.  While on, vxrt_get_stats cannot separate the passes: ms_primary reads as the whole frame, ms_shadow as 0. */
 int vxrt_set_overlap(vxrt_ctx* ctx, int mode);
+/* Fusion of the two passes: 0 two kernels per frame (primary pass, then shade pass over the hit slots), 1 one kernel per frame
+   in which every block traces its tile's primary rays and then shades its own hits (hit records stay in shared memory),
+   2 auto (default): fused when this context renders <= 12,000 tiles.  For a small share the frame time is set by serial
+   chains (the longest primary ray, then the longest pixel's sequential light loop); with a kernel boundary between the
+   passes the two chains add, fused they overlap.  On a whole 4K frame the two specialised kernels (40 / 48 registers, 6 / 5
+   blocks per SM) have the higher throughput.  Same pixels.  While fused, vxrt_get_stats cannot separate the passes
+   (ms_primary = whole frame, ms_shadow = 0), and vxrt_set_overlap has no effect. */
+int vxrt_set_fusion(vxrt_ctx* ctx, int mode);
 /* mode 0 (default) = the production kernels: no per-iteration counter, rays that cannot change a pixel are not traced
    (vxrt_set_culling); vxrt_get_stats then reads rays_local / fetches / rays_dark as 0 while hit_pixels, rays_primary,
    rays_global and the timings stay valid.  mode 1: every vxrt_render runs the counted kernel variants by the REFERENCE's

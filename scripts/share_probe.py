@@ -30,7 +30,7 @@ ren.updateUniforms(frame)
 
 
 def timed(label, **sw):
-    ren.setOverlap(sw.get("overlap", 0)); ren.setTraversal(sw.get("trav", True)); ren.setL2Prefetch(sw.get("l2", 2))
+    ren.setFusion(sw.get("fused", 0)); ren.setOverlap(sw.get("overlap", 0)); ren.setTraversal(sw.get("trav", True)); ren.setL2Prefetch(sw.get("l2", 2))
     ren.setTileOrdering(sw.get("order", True))
     for _ in range(30):
         ren.draw()
@@ -48,14 +48,18 @@ def timed(label, **sw):
     return out
 
 
-res = [timed("baseline: overlap off, traversal on, L2 sweep auto, ordering on"),
+res = [timed("fused, L2 sweep auto", fused=1),
+       timed("fused, L2 sweep off", fused=1, l2=0),
+       timed("fused, L2 sweep off, traversal off", fused=1, l2=0, trav=False),
+       timed("fused, L2 sweep off, ordering off", fused=1, l2=0, order=False),
+       timed("two passes: overlap off, traversal on, L2 sweep auto, ordering on"),
        timed("overlap on", overlap=1),
        timed("traversal off", trav=False),
        timed("traversal off, overlap on", trav=False, overlap=1),
        timed("L2 sweep off", l2=0),
        timed("ordering off", order=False),
        timed("ordering off, overlap on", order=False, overlap=1)]
-ren.setOverlap(0); ren.setTraversal(True); ren.setL2Prefetch(2); ren.setTileOrdering(True)
+ren.setFusion(0); ren.setOverlap(0); ren.setTraversal(True); ren.setL2Prefetch(2); ren.setTileOrdering(True)
 for _ in range(10):
     ren.draw()
 ren.sync()
@@ -74,6 +78,12 @@ def dist(c):
 
 
 print(json.dumps({"primary_blocks": dist(pc), "shade_blocks": dist(sc), "tiles": int(pc.size)}))
+ren.setFusion(1); ren.setL2Prefetch(0)
+for _ in range(10):
+    ren.draw()
+ren.sync()
+fc, _ = ren.blockCosts()
+print(json.dumps({"fused_blocks": dist(fc)}))
 del flush
 torch.cuda.synchronize()
 ren.close()

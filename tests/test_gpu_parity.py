@@ -279,6 +279,7 @@ def test_render_is_idempotent_and_view_toggle(vx, ren):
     W, H = 160, 90
     ren.reshape(W, H)
     ren.setL2Prefetch(0)                                             # (its sweep kernel would add one launch per frame)
+    ren.setFusion(0)                                                 # two passes: the launch counts below are theirs
     fr = to_vx_frame(vx, gc.frame_cases(W, H)["C2"])
     a = ren.renderFrameHost(fr)
     b = ren.renderFrameHost(fr)
@@ -309,6 +310,15 @@ def test_render_is_idempotent_and_view_toggle(vx, ren):
     ren.setL2Prefetch(1)                                             # the cold-L2 sweep: one more launch, same pixels
     ren.draw()
     assert ren.stats()["kernel_launches"] == 3 and np.array_equal(ren.readPixels(), want)
+    ren.setL2Prefetch(0)
+    ren.setFusion(1)                                                 # one fused kernel per frame (+ the order refresh on frames 0, 1, 8, ...)
+    launches = []
+    for _ in range(10):
+        ren.draw()
+        launches.append(ren.stats()["kernel_launches"])
+        assert np.array_equal(ren.readPixels(), want)
+    assert launches[0] == 2 and launches[1] == 2 and launches[2] == 1 and launches[8] == 2
+    ren.setFusion(2)
     ren.setL2Prefetch(2)
 
 
@@ -957,9 +967,10 @@ def test_stats_modes_count_the_reference_rule_and_the_executed_work(vx, oracle, 
                 r.setStats(3)
 
 
-def test_overlapped_passes_render_the_same_frames(vx, oracle, default_level):
-    """vxrt_set_overlap: the shade kernel is launched with programmatic stream serialization and starts inside the primary pass's
-    tail; its blocks wait for their tile's ready flag.  Same pixels as the oracle for production and counted kernels, across
+def test_fused_and_overlapped_frames_render_the_same_pixels(vx, oracle, default_level):
+    """vxrt_set_fusion: one kernel per frame, every block traces its tile's primary rays and then shades its own hits;
+    vxrt_set_overlap: two kernels, the shade kernel launched with programmatic stream serialization, its blocks wait for their
+    tile's ready flag.  Same pixels as the oracle for production and counted kernels, across
     frames that differ (a stale flag or hit slot would show), frame sizes, launch orders and a tile-partition context"""
     level = default_level
     for W, H in ((640, 360), (1920, 1080), (100, 37)):
@@ -968,7 +979,8 @@ def test_overlapped_passes_render_the_same_frames(vx, oracle, default_level):
         with vx.Renderer(grid=gc.DIMS, width=W, height=H) as r:
             r.updateGeometry(level)
             out = r.hostFrameBuffer()
-            for mode in (1, 0, 2):
+            for fusion, mode in ((0, 1), (0, 0), (0, 2), (1, 0), (2, 0)):       # two passes (overlapped / not / auto), fused, auto
+                r.setFusion(fusion)
                 r.setOverlap(mode)
                 for stats in (0, 1):
                     r.setStats(stats)
@@ -977,8 +989,9 @@ def test_overlapped_passes_render_the_same_frames(vx, oracle, default_level):
                         r.draw()                                             # whole-frame launch: the overlapped path
                         got = r.readPixels()
                         bad = int((got != want[n]).any(axis=2).sum())
-                        assert bad == 0, (W, H, mode, stats, k, n, bad)
+                        assert bad == 0, (W, H, fusion, mode, stats, k, n, bad)
             r.setStats(0)
+            r.setFusion(0)
             r.setOverlap(1)
             out[:] = 0x5A
             r.renderFrameHost(to_vx_frame(vx, gc.frame_cases(W, H)["C2"]), out)   # banded path: not overlapped, same pixels
@@ -990,6 +1003,7 @@ def test_overlapped_passes_render_the_same_frames(vx, oracle, default_level):
     for rank in range(world):
         with vx.Renderer(grid=gc.DIMS, width=W, height=H, rank=rank, world=world) as r:
             r.updateGeometry(level)
+            r.setFusion(rank % 2)                                                # ranks may even differ in how they schedule their tiles
             r.setOverlap(1)
             r.updateUniforms(to_vx_frame(vx, fr))
             for _ in range(3):

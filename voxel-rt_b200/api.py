@@ -86,6 +86,7 @@ _SIGNATURES = {
     "vxrt_set_culling": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_tile_ordering": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
+    "vxrt_set_fusion": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_render_frame_host": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p]),
     "vxrt_submit_frame_host": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p]),
@@ -386,6 +387,10 @@ class Renderer:
 
     def setCulling(self, enabled):
         self._check(self.lib.vxrt_set_culling(self._h, 1 if enabled else 0))
+
+    def setFusion(self, mode):
+        """0 two kernels per frame, 1 one fused kernel (a block traces its tile's primary rays, then shades its own hits), 2 auto"""
+        self._check(self.lib.vxrt_set_fusion(self._h, int(mode)))
 
     def setOverlap(self, mode):
         """0 off, 1 on, 2 auto (default): the shade pass starts inside the primary pass's tail (programmatic dependent launch)"""

@@ -77,6 +77,51 @@ __device__ __forceinline__ uint32_t out_index_of(const TileMap& m, int raster, i
 // COUNT: maintain the per-ray iteration counter (needed by the step-count view, the debug planes and the fetch
 // statistics); the production frame path runs without it.
 // TRAV: g.vox is the traversal grid (trav.cuh)
+
+// fshader.glsl:131-145 for the pixel of this thread: ray set-up, primary castRay, misses / the step-count view finished here.
+// Returns true when the pixel hit a voxel (its lighting follows, fshader.glsl:147-187).
+template <bool COUNT, class Grid, bool TRAV>
+__device__ __forceinline__ bool primary_pixel(const Grid& g, const FrameParams& f, const TileMap& m, const Outputs& o, int local_tile,
+                                              int warp, int lane, RayHit& r, uint32_t& pid) {
+    const int t = local_tile * m.world + m.rank;                    // global tile
+    const int lx = (warp & 3) * 8 + (lane & 7), ly = (warp >> 2) * 4 + (lane >> 3);
+    const int px = (t % m.tx) * TILE_W + lx, py = (t / m.tx) * TILE_H + ly;
+    const bool valid = (t < m.ntiles) && (px < m.width) && (py < m.height);
+    bool hit = false;
+    r.steps = 0; r.idx = -1;
+    pid = (uint32_t)(py * m.width + px);
+    if (valid) {
+        // vshader.glsl:6-9 + quad render.cpp:36-44: vPos = NDC of the pixel centre
+        const float vx = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn((float)px, 0.5f), (float)m.width), 2.0f), 1.0f);
+        const float vy = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn((float)py, 0.5f), (float)m.height), 2.0f), 1.0f);
+        float dxn = __fmul_rn(vx, f.aspect), dyn = vy, dzn = 1.0f;   // :136
+        normalize3(dxn, dyn, dzn);
+        // :137  mat4 * vec4(dir,0) = (m[0]*v0 + m[1]*v1) + (m[2]*v2 + m[3]*0)   (GLM type_mat4x4.inl:561-572)
+        const float* M = f.rotate;
+        const float rx = __fadd_rn(__fadd_rn(__fmul_rn(M[0], dxn), __fmul_rn(M[4], dyn)), __fadd_rn(__fmul_rn(M[8], dzn), __fmul_rn(M[12], 0.0f)));
+        const float ry = __fadd_rn(__fadd_rn(__fmul_rn(M[1], dxn), __fmul_rn(M[5], dyn)), __fadd_rn(__fmul_rn(M[9], dzn), __fmul_rn(M[13], 0.0f)));
+        const float rz = __fadd_rn(__fadd_rn(__fmul_rn(M[2], dxn), __fmul_rn(M[6], dyn)), __fadd_rn(__fmul_rn(M[10], dzn), __fmul_rn(M[14], 0.0f)));
+        r = cast_ray<COUNT, false, true, Grid, TRAV>(g, f.cam_pos[0], f.cam_pos[1], f.cam_pos[2], rx, ry, rz, VXRT_RENDER_DIST);   // :139
+        if (f.view_depth_field == 1) {                               // :143-145
+            const float grey = __fdiv_rn((float)r.steps, 100.0f);
+            o.rgba8[out_index_of(m, o.raster, px, py)] = pack_rgba8(grey, grey, grey, 1.0f);
+        } else if (r.idx >= 0) {
+            hit = true;                                              // lighting follows
+        } else {
+            o.rgba8[out_index_of(m, o.raster, px, py)] = pack_rgba8(0.6f, 0.7f, 0.8f, 1.0f);   // :133
+        }
+        if (o.dbg_hit) {
+            o.dbg_hit[pid] = r.idx;
+            o.dbg_steps[pid] = (uint16_t)(r.steps > 65535 ? 65535 : r.steps);
+            if (!hit) { o.dbg_occl[pid] = 0u; o.dbg_cast[pid] = 0u; }
+        }
+    }
+    return hit;
+}
+__device__ __forceinline__ float4 hit_record(const RayHit& r) {     // hitPos.xyz, w = colour(24) | normal(4) << 24
+    return make_float4(r.hx, r.hy, r.hz, __uint_as_float(((uint32_t)r.voxel & 0x00FFFFFFu) | ((uint32_t)r.normal << 24)));
+}
+
 template <bool COUNT, class Grid, bool TRAV>
 __global__ void __launch_bounds__(256, 6) primary_kernel(Grid g, const __grid_constant__ FrameParams f,
                                                       TileMap m, Outputs o) {
@@ -91,40 +136,9 @@ __global__ void __launch_bounds__(256, 6) primary_kernel(Grid g, const __grid_co
     // blocks are handed out in launch order: with a tile order from the previous frame the slowest tiles start first,
     // which shortens the kernel's tail (it matters once a GPU renders only 1/4 or 1/8 of the frame)
     const int local_tile = o.tile_order ? (int)o.tile_order[blockIdx.x] : (int)blockIdx.x + m.tile_base;
-    const int t = local_tile * m.world + m.rank;                    // global tile
-    const int lx = (warp & 3) * 8 + (lane & 7), ly = (warp >> 2) * 4 + (lane >> 3);
-    const int px = (t % m.tx) * TILE_W + lx, py = (t / m.tx) * TILE_H + ly;
-    const bool valid = (t < m.ntiles) && (px < m.width) && (py < m.height);
-
-    bool hit = false;
-    RayHit r; r.steps = 0; r.idx = -1;
-    if (valid) {
-        // vshader.glsl:6-9 + quad render.cpp:36-44: vPos = NDC of the pixel centre
-        const float vx = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn((float)px, 0.5f), (float)m.width), 2.0f), 1.0f);
-        const float vy = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn((float)py, 0.5f), (float)m.height), 2.0f), 1.0f);
-        float dxn = __fmul_rn(vx, f.aspect), dyn = vy, dzn = 1.0f;   // :136
-        normalize3(dxn, dyn, dzn);
-        // :137  mat4 * vec4(dir,0) = (m[0]*v0 + m[1]*v1) + (m[2]*v2 + m[3]*0)   (GLM type_mat4x4.inl:561-572)
-        const float* M = f.rotate;
-        const float rx = __fadd_rn(__fadd_rn(__fmul_rn(M[0], dxn), __fmul_rn(M[4], dyn)), __fadd_rn(__fmul_rn(M[8], dzn), __fmul_rn(M[12], 0.0f)));
-        const float ry = __fadd_rn(__fadd_rn(__fmul_rn(M[1], dxn), __fmul_rn(M[5], dyn)), __fadd_rn(__fmul_rn(M[9], dzn), __fmul_rn(M[13], 0.0f)));
-        const float rz = __fadd_rn(__fadd_rn(__fmul_rn(M[2], dxn), __fmul_rn(M[6], dyn)), __fadd_rn(__fmul_rn(M[10], dzn), __fmul_rn(M[14], 0.0f)));
-        r = cast_ray<COUNT, false, true, Grid, TRAV>(g, f.cam_pos[0], f.cam_pos[1], f.cam_pos[2], rx, ry, rz, VXRT_RENDER_DIST);   // :139
-        const uint32_t pid = (uint32_t)(py * m.width + px);
-        if (f.view_depth_field == 1) {                               // :143-145
-            const float grey = __fdiv_rn((float)r.steps, 100.0f);
-            o.rgba8[out_index_of(m, o.raster, px, py)] = pack_rgba8(grey, grey, grey, 1.0f);
-        } else if (r.idx >= 0) {
-            hit = true;                                              // finished by shade_kernel
-        } else {
-            o.rgba8[out_index_of(m, o.raster, px, py)] = pack_rgba8(0.6f, 0.7f, 0.8f, 1.0f);   // :133
-        }
-        if (o.dbg_hit) {
-            o.dbg_hit[pid] = r.idx;
-            o.dbg_steps[pid] = (uint16_t)(r.steps > 65535 ? 65535 : r.steps);
-            if (!hit) { o.dbg_occl[pid] = 0u; o.dbg_cast[pid] = 0u; }
-        }
-    }
+    RayHit r;
+    uint32_t pid;
+    const bool hit = primary_pixel<COUNT, Grid, TRAV>(g, f, m, o, local_tile, warp, lane, r, pid);
     // ---- hit compaction into the tile's 256 slots: warp ballot -> block prefix (no global ordering: the shade pass
     //      schedules tiles by its own cost feedback) ---------------------------------------------------------------
     const unsigned ballot = __ballot_sync(0xffffffffu, hit);
@@ -142,8 +156,8 @@ __global__ void __launch_bounds__(256, 6) primary_kernel(Grid g, const __grid_co
     __syncthreads();
     if (hit) {
         const unsigned pos = (unsigned)local_tile * TILE_PIX + s_warp_hits[warp] + __popc(ballot & ((1u << lane) - 1u));
-        o.hitq[pos] = make_float4(r.hx, r.hy, r.hz, __uint_as_float(((uint32_t)r.voxel & 0x00FFFFFFu) | ((uint32_t)r.normal << 24)));
-        o.hitpix[pos] = (uint32_t)(py * m.width + px);
+        o.hitq[pos] = hit_record(r);
+        o.hitpix[pos] = pid;
     }
     if (tid == 0 && s_fetches) atomicAdd(&o.counters->fetches_primary, s_fetches);
     if (tid == 0 && o.tile_cost) o.tile_cost[local_tile] = (uint32_t)min((long long)0xffffffffll, clock64() - t_start);
@@ -206,12 +220,114 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __rest
 }
 
 // TRAV: g.vox is the traversal grid (trav.cuh): shadow / light rays take the runs its band words promise
+
+struct LightList {                      // active lights of the frame, compacted (slot order preserved), in shared memory
+    float4 light[16];
+    int slot[16];
+    int nactive;
+};
+// first warp of the block: fshader.glsl:167, a slot is in the scene iff x,y,z >= 0 (a barrier must follow)
+__device__ __forceinline__ void compact_lights(const FrameParams& f, LightList& L, int tid, int lane) {
+    if (tid < 32) {
+        const bool act = (tid < 16) && f.lights[tid & 15][0] >= 0.0f && f.lights[tid & 15][1] >= 0.0f && f.lights[tid & 15][2] >= 0.0f;
+        const unsigned b = __ballot_sync(0xffffffffu, act);
+        if (act) {
+            const int k = __popc(b & ((1u << lane) - 1u));
+            L.light[k] = make_float4(f.lights[tid][0], f.lights[tid][1], f.lights[tid][2], f.lights[tid][3]);
+            L.slot[k] = tid;
+        }
+        if (tid == 0) L.nactive = __popc(b);
+    }
+}
+struct ShadeCounts { unsigned fetches, nlocal, ndark, nglobal; };
+
+// fshader.glsl:147-187 for one hit pixel: global-light shadow ray, the sequential local-light loop, colour, store
+template <bool COUNT, class Grid, bool TRAV>
+__device__ __forceinline__ void shade_pixel(const Grid& g, const FrameParams& f, const TileMap& m, const Outputs& o, const LightList& LL,
+                                            const float4 rec, const uint32_t pid, ShadeCounts& n) {
+    const uint32_t packed = __float_as_uint(rec.w);
+    float nx, ny, nz;
+    unpack_normal((int)(packed >> 24), nx, ny, nz);
+    const float hx = rec.x, hy = rec.y, hz = rec.z;
+    // Rays toward a light the surface faces away from (N.L <= 0) add exactly +-0 to the multiplier whether they
+    // are occluded or not (fshader.glsl:155,177: "* max(0, dot(N, L))"), so production frames do not trace them; the
+    // sign test uses the unnormalised direction (normalising multiplies by a positive number).  Counted variants
+    // (statistics / debug planes) trace every ray the reference casts and report how many were of this kind, unless
+    // the host asks them to count what the production kernels execute (skip_dark set: rays_dark = rays skipped).
+    const bool skip_dark = o.skip_dark != 0;
+    // :147
+    float lx = __fsub_rn(f.light_pos[0], hx), ly = __fsub_rn(f.light_pos[1], hy), lz = __fsub_rn(f.light_pos[2], hz);
+    const bool g_lit = dot3(nx, ny, nz, lx, ly, lz) > 0.0f;
+    float multiplier = VXRT_AMBIENT;                             // :149
+    uint32_t occl = 0u, cast = 1u;
+    if (COUNT && !g_lit) n.ndark++;
+    if (g_lit || !skip_dark) {   // :154 global-light shadow ray
+        if (COUNT) n.nglobal++;
+        normalize3(lx, ly, lz);
+        const RayHit s = cast_ray<COUNT, true, true, Grid, TRAV>(g, __fadd_rn(hx, __fmul_rn(lx, 0.001f)), __fadd_rn(hy, __fmul_rn(ly, 0.001f)),
+                                  __fadd_rn(hz, __fmul_rn(lz, 0.001f)), lx, ly, lz, VXRT_RENDER_DIST);
+        n.fetches += (unsigned)s.steps;
+        if (s.idx == -1) multiplier = __fadd_rn(multiplier, __fmul_rn(VXRT_DIFFUSE, max0(dot3(nx, ny, nz, lx, ly, lz))));   // :155
+        else occl |= 1u;
+    }
+    // :159-181.  The reference walks slots 0..15 and tests the overbright clamp at the TOP of every
+    // iteration (active slot or not); walking only the active slots is equivalent when the clamp is also
+    // applied for the inactive iterations that follow the last active slot.
+    const int nact = LL.nactive;
+    int last_slot = -1;
+    bool broke = false;
+    for (int k = 0; k < nact; k++) {
+        if (multiplier >= VXRT_MAX_OVERBRIGHT) { multiplier = VXRT_MAX_OVERBRIGHT; broke = true; break; }   // :161-164
+        const float4 L = LL.light[k];
+        const int slot = LL.slot[k];
+        last_slot = slot;
+        float tx = __fsub_rn(L.x, hx), ty = __fsub_rn(L.y, hy), tz = __fsub_rn(L.z, hz);
+        // (a non-finite weight would turn the +-0 into NaN: such a light is always traced)
+        const bool lit = dot3(nx, ny, nz, tx, ty, tz) > 0.0f || !(fabsf(L.w) <= 3.0e38f);
+        if (!COUNT && skip_dark && !lit) continue;
+        const float lld = __fsqrt_rn(dot3(tx, ty, tz, tx, ty, tz));                      // :168
+        if (lld <= (float)VXRT_LOCAL_LIGHT_DIST) {                                       // :171
+            if (COUNT && !lit) { n.ndark++; if (skip_dark) continue; }
+            normalize3_with_length(tx, ty, tz, lld);                                    // :173 (same dot, same sqrt as :168)
+            cast |= 2u << slot; n.nlocal++;
+            const RayHit s = cast_ray<COUNT, true, false, Grid, TRAV>(g, __fadd_rn(hx, __fmul_rn(tx, 0.001f)), __fadd_rn(hy, __fmul_rn(ty, 0.001f)),
+                                      __fadd_rn(hz, __fmul_rn(tz, 0.001f)), tx, ty, tz, f2i(__fadd_rn(lld, 1.0f)));   // :175
+            n.fetches += (unsigned)s.steps;
+            if (s.idx == -1) {                                                          // :177
+                // (64 - d) / 64: dividing by a power of two is an exact scaling, identical to the IEEE quotient
+                const float fall = __fmul_rn(__fsub_rn((float)VXRT_LOCAL_LIGHT_DIST, lld), 1.0f / (float)VXRT_LOCAL_LIGHT_DIST);
+                multiplier = __fadd_rn(multiplier, __fmul_rn(__fmul_rn(L.w, max0(dot3(nx, ny, nz, tx, ty, tz))), fall));
+            } else occl |= 2u << slot;
+        }
+    }
+    if (!broke && last_slot < 15 && multiplier >= VXRT_MAX_OVERBRIGHT) multiplier = VXRT_MAX_OVERBRIGHT;
+    // :184-187
+    const float cr = __fmul_rn(__fdiv_rn((float)((packed >> 16) & 255u), 255.0f), multiplier);
+    const float cg = __fmul_rn(__fdiv_rn((float)((packed >> 8) & 255u), 255.0f), multiplier);
+    const float cb = __fmul_rn(__fdiv_rn((float)(packed & 255u), 255.0f), multiplier);
+    const int px = (int)(pid % (uint32_t)m.width), py = (int)(pid / (uint32_t)m.width);
+    o.rgba8[out_index_of(m, o.raster, px, py)] = pack_rgba8(cr, cg, cb, 1.0f);
+    if (o.dbg_occl) { o.dbg_occl[pid] = occl; o.dbg_cast[pid] = cast; }
+}
+// block-level sums of the shade counters into the frame's counters (s_fetches / s_local: zeroed shared scratch; ends with a barrier)
+template <bool COUNT>
+__device__ __forceinline__ void shade_counts_to_global(const Outputs& o, const ShadeCounts& n, unsigned long long& s_fetches,
+                                                       unsigned long long& s_local, int tid, int lane) {
+    const unsigned wf = __reduce_add_sync(0xffffffffu, n.fetches), wl = __reduce_add_sync(0xffffffffu, n.nlocal);
+    if (COUNT) {
+        const unsigned wd = __reduce_add_sync(0xffffffffu, n.ndark), wg = __reduce_add_sync(0xffffffffu, n.nglobal);
+        if (lane == 0 && wd) atomicAdd(&o.counters->rays_dark, (unsigned long long)wd);
+        if (lane == 0 && wg) atomicAdd(&o.counters->global_traced, wg);
+    }
+    if (lane == 0 && wf) { atomicAdd(&s_fetches, (unsigned long long)wf); atomicAdd(&s_local, (unsigned long long)wl); }
+    __syncthreads();
+    if (tid == 0 && s_fetches) { atomicAdd(&o.counters->fetches_shadow, s_fetches); atomicAdd(&o.counters->rays_local, s_local); }
+}
+
 template <bool COUNT, class Grid, bool TRAV>
 __global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_constant__ FrameParams f,
                                                     TileMap m, Outputs o) {
-    __shared__ float4 s_light[16];          // compacted active lights (slot order preserved)
-    __shared__ int s_slot[16];
-    __shared__ int s_nactive;
+    __shared__ LightList s_lights;
     __shared__ unsigned long long s_fetches, s_local;
     const int tid = threadIdx.x, lane = tid & 31;
     // a shade unit = blockDim.x consecutive slots of one tile; units are launched slowest-first (previous frame's times)
@@ -240,97 +356,63 @@ __global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_cons
         if (tid == 0 && o.shade_cost) o.shade_cost[unit] = 0u;
         return;
     }
-    if (tid < 32) {
-        // fshader.glsl:167: a slot is in the scene iff x,y,z >= 0
-        const bool act = (tid < 16) && f.lights[tid & 15][0] >= 0.0f && f.lights[tid & 15][1] >= 0.0f && f.lights[tid & 15][2] >= 0.0f;
-        const unsigned b = __ballot_sync(0xffffffffu, act);
-        if (act) {
-            const int k = __popc(b & ((1u << lane) - 1u));
-            s_light[k] = make_float4(f.lights[tid][0], f.lights[tid][1], f.lights[tid][2], f.lights[tid][3]);
-            s_slot[k] = tid;
-        }
-        if (tid == 0) { s_nactive = __popc(b); s_fetches = 0ull; s_local = 0ull; }
-    }
+    compact_lights(f, s_lights, tid, lane);
+    if (tid == 0) { s_fetches = 0ull; s_local = 0ull; }
     __syncthreads();
     const unsigned i = (unsigned)tile * TILE_PIX + (unsigned)slot;
-    unsigned fetches = 0, nlocal = 0, ndark = 0, nglobal = 0;
-    if ((unsigned)slot < count) {
-        const float4 rec = o.hitq[i];
-        const uint32_t pid = o.hitpix[i];
-        const uint32_t packed = __float_as_uint(rec.w);
-        float nx, ny, nz;
-        unpack_normal((int)(packed >> 24), nx, ny, nz);
-        const float hx = rec.x, hy = rec.y, hz = rec.z;
-        // Rays toward a light the surface faces away from (N.L <= 0) add exactly +-0 to the multiplier whether they
-        // are occluded or not (fshader.glsl:155,177: "* max(0, dot(N, L))"), so production frames do not trace them; the
-        // sign test uses the unnormalised direction (normalising multiplies by a positive number).  Counted variants
-        // (statistics / debug planes) trace every ray the reference casts and report how many were of this kind, unless
-        // the host asks them to count what the production kernels execute (skip_dark set: rays_dark = rays skipped).
-        const bool skip_dark = o.skip_dark != 0;
-        // :147
-        float lx = __fsub_rn(f.light_pos[0], hx), ly = __fsub_rn(f.light_pos[1], hy), lz = __fsub_rn(f.light_pos[2], hz);
-        const bool g_lit = dot3(nx, ny, nz, lx, ly, lz) > 0.0f;
-        float multiplier = VXRT_AMBIENT;                             // :149
-        uint32_t occl = 0u, cast = 1u;
-        if (COUNT && !g_lit) ndark++;
-        if (g_lit || !skip_dark) {   // :154 global-light shadow ray
-            if (COUNT) nglobal++;
-            normalize3(lx, ly, lz);
-            const RayHit s = cast_ray<COUNT, true, true, Grid, TRAV>(g, __fadd_rn(hx, __fmul_rn(lx, 0.001f)), __fadd_rn(hy, __fmul_rn(ly, 0.001f)),
-                                      __fadd_rn(hz, __fmul_rn(lz, 0.001f)), lx, ly, lz, VXRT_RENDER_DIST);
-            fetches += (unsigned)s.steps;
-            if (s.idx == -1) multiplier = __fadd_rn(multiplier, __fmul_rn(VXRT_DIFFUSE, max0(dot3(nx, ny, nz, lx, ly, lz))));   // :155
-            else occl |= 1u;
-        }
-        // :159-181.  The reference walks slots 0..15 and tests the overbright clamp at the TOP of every
-        // iteration (active slot or not); walking only the active slots is equivalent when the clamp is also
-        // applied for the inactive iterations that follow the last active slot.
-        const int nact = s_nactive;
-        int last_slot = -1;
-        bool broke = false;
-        for (int k = 0; k < nact; k++) {
-            if (multiplier >= VXRT_MAX_OVERBRIGHT) { multiplier = VXRT_MAX_OVERBRIGHT; broke = true; break; }   // :161-164
-            const float4 L = s_light[k];
-            const int slot = s_slot[k];
-            last_slot = slot;
-            float tx = __fsub_rn(L.x, hx), ty = __fsub_rn(L.y, hy), tz = __fsub_rn(L.z, hz);
-            // (a non-finite weight would turn the +-0 into NaN: such a light is always traced)
-            const bool lit = dot3(nx, ny, nz, tx, ty, tz) > 0.0f || !(fabsf(L.w) <= 3.0e38f);
-            if (!COUNT && skip_dark && !lit) continue;
-            const float lld = __fsqrt_rn(dot3(tx, ty, tz, tx, ty, tz));                      // :168
-            if (lld <= (float)VXRT_LOCAL_LIGHT_DIST) {                                       // :171
-                if (COUNT && !lit) { ndark++; if (skip_dark) continue; }
-                normalize3_with_length(tx, ty, tz, lld);                                    // :173 (same dot, same sqrt as :168)
-                cast |= 2u << slot; nlocal++;
-                const RayHit s = cast_ray<COUNT, true, false, Grid, TRAV>(g, __fadd_rn(hx, __fmul_rn(tx, 0.001f)), __fadd_rn(hy, __fmul_rn(ty, 0.001f)),
-                                          __fadd_rn(hz, __fmul_rn(tz, 0.001f)), tx, ty, tz, f2i(__fadd_rn(lld, 1.0f)));   // :175
-                fetches += (unsigned)s.steps;
-                if (s.idx == -1) {                                                          // :177
-                    // (64 - d) / 64: dividing by a power of two is an exact scaling, identical to the IEEE quotient
-                    const float fall = __fmul_rn(__fsub_rn((float)VXRT_LOCAL_LIGHT_DIST, lld), 1.0f / (float)VXRT_LOCAL_LIGHT_DIST);
-                    multiplier = __fadd_rn(multiplier, __fmul_rn(__fmul_rn(L.w, max0(dot3(nx, ny, nz, tx, ty, tz))), fall));
-                } else occl |= 2u << slot;
-            }
-        }
-        if (!broke && last_slot < 15 && multiplier >= VXRT_MAX_OVERBRIGHT) multiplier = VXRT_MAX_OVERBRIGHT;
-        // :184-187
-        const float cr = __fmul_rn(__fdiv_rn((float)((packed >> 16) & 255u), 255.0f), multiplier);
-        const float cg = __fmul_rn(__fdiv_rn((float)((packed >> 8) & 255u), 255.0f), multiplier);
-        const float cb = __fmul_rn(__fdiv_rn((float)(packed & 255u), 255.0f), multiplier);
-        const int px = (int)(pid % (uint32_t)m.width), py = (int)(pid / (uint32_t)m.width);
-        o.rgba8[out_index_of(m, o.raster, px, py)] = pack_rgba8(cr, cg, cb, 1.0f);
-        if (o.dbg_occl) { o.dbg_occl[pid] = occl; o.dbg_cast[pid] = cast; }
-    }
-    const unsigned wf = __reduce_add_sync(0xffffffffu, fetches), wl = __reduce_add_sync(0xffffffffu, nlocal);
-    if (COUNT) {
-        const unsigned wd = __reduce_add_sync(0xffffffffu, ndark), wg = __reduce_add_sync(0xffffffffu, nglobal);
-        if (lane == 0 && wd) atomicAdd(&o.counters->rays_dark, (unsigned long long)wd);
-        if (lane == 0 && wg) atomicAdd(&o.counters->global_traced, wg);
-    }
-    if (lane == 0 && wf) { atomicAdd(&s_fetches, (unsigned long long)wf); atomicAdd(&s_local, (unsigned long long)wl); }
-    __syncthreads();
-    if (tid == 0 && s_fetches) { atomicAdd(&o.counters->fetches_shadow, s_fetches); atomicAdd(&o.counters->rays_local, s_local); }
+    ShadeCounts n = {0u, 0u, 0u, 0u};
+    if ((unsigned)slot < count) shade_pixel<COUNT, Grid, TRAV>(g, f, m, o, s_lights, o.hitq[i], o.hitpix[i], n);
+    shade_counts_to_global<COUNT>(o, n, s_fetches, s_local, tid, lane);
     if (tid == 0 && o.shade_cost) o.shade_cost[unit] = (uint32_t)min((long long)0xffffffffll, clock64() - t_start);
+}
+
+// The whole of fshader.glsl's main() for one tile in ONE block: primary rays, hit compaction in shared memory, then the block
+// shades its own hits.  Used when a context renders a small share of the frame (vxrt_set_fusion, auto): there the frame time is set
+// by the serial chains -- the longest primary ray (~50 us), then the longest pixel's sequential light loop (~100 us) -- and a
+// kernel boundary between the passes makes the two add; fused, a tile's lighting starts the moment its own primary rays are done,
+// and blocks launch slowest-first by their combined time.  No hit slots in global memory, one launch.
+template <bool COUNT, class Grid, bool TRAV>
+__global__ void __launch_bounds__(256, 5) frame_kernel(Grid g, const __grid_constant__ FrameParams f,
+                                                    TileMap m, Outputs o) {
+    __shared__ LightList s_lights;
+    __shared__ float4 s_hit[TILE_PIX];
+    __shared__ uint32_t s_pix[TILE_PIX];
+    __shared__ unsigned int s_warp_hits[8];
+    __shared__ unsigned int s_total;
+    __shared__ unsigned long long s_fetches, s_local, s_fetches_primary;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long t_start = clock64();
+    const int local_tile = o.tile_order ? (int)o.tile_order[blockIdx.x] : (int)blockIdx.x + m.tile_base;
+    compact_lights(f, s_lights, tid, lane);
+    if (tid == 0) { s_fetches = 0ull; s_local = 0ull; s_fetches_primary = 0ull; }
+    RayHit r;
+    uint32_t pid;
+    const bool hit = primary_pixel<COUNT, Grid, TRAV>(g, f, m, o, local_tile, warp, lane, r, pid);
+    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    const unsigned wfetch = __reduce_add_sync(0xffffffffu, (unsigned)r.steps);
+    if (lane == 0) s_warp_hits[warp] = __popc(ballot);
+    __syncthreads();
+    if (lane == 0 && wfetch) atomicAdd(&s_fetches_primary, (unsigned long long)wfetch);
+    if (tid == 0) {
+        unsigned total = 0;
+        #pragma unroll
+        for (int w = 0; w < 8; w++) { const unsigned c = s_warp_hits[w]; s_warp_hits[w] = total; total += c; }
+        s_total = total;
+        o.tile_hits[local_tile] = total;
+        if (total) atomicAdd(&o.counters->hit_count, total);          // statistics only
+    }
+    __syncthreads();
+    if (hit) {
+        const unsigned pos = s_warp_hits[warp] + __popc(ballot & ((1u << lane) - 1u));
+        s_hit[pos] = hit_record(r);
+        s_pix[pos] = pid;
+    }
+    __syncthreads();
+    if (tid == 0 && s_fetches_primary) atomicAdd(&o.counters->fetches_primary, s_fetches_primary);
+    ShadeCounts n = {0u, 0u, 0u, 0u};
+    if (f.view_depth_field != 1 && (unsigned)tid < s_total) shade_pixel<COUNT, Grid, TRAV>(g, f, m, o, s_lights, s_hit[tid], s_pix[tid], n);
+    shade_counts_to_global<COUNT>(o, n, s_fetches, s_local, tid, lane);
+    if (tid == 0 && o.tile_cost) o.tile_cost[local_tile] = (uint32_t)min((long long)0xffffffffll, clock64() - t_start);
 }
 
 // ------------------------------------------------------------------------------------------------

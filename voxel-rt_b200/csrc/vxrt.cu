@@ -85,7 +85,9 @@ struct vxrt_ctx {
     int order_shade_threads = 0;        // block size the shade order was recorded with
     unsigned long long order_frame = 0; // whole-frame launches since the ordering was (re)started
     bool use_tile_order = true;
-    int overlap = 2;                    // vxrt_set_overlap: 0 off, 1 on, 2 auto (on when this context renders <= 12,000 tiles) -- the shade
+    int fusion = 2;                     // vxrt_set_fusion: 0 two passes, 1 one fused kernel per frame, 2 auto (fused when this context renders
+                                        // <= 12,000 tiles: a tile's lighting then starts the moment its own primary rays are done)
+    int overlap = 0;                    // vxrt_set_overlap: 0 off (default), 1 on, 2 auto (on when this context renders <= 12,000 tiles) -- the shade
                                         // pass starts inside the primary pass's tail (programmatic dependent launch + per-tile flags)
     uint32_t* d_tile_ready = nullptr;   // per local tile: frame_seq of the last primary pass that finished it
     int* d_overlap_err = nullptr;
@@ -393,6 +395,7 @@ extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     if (const char* e = getenv("VXRT_L2_PREFETCH")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->l2_prefetch = v; }
     if (const char* e = getenv("VXRT_TRAVERSAL")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->trav_mode = v; }
     if (const char* e = getenv("VXRT_OVERLAP")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->overlap = v; }
+    if (const char* e = getenv("VXRT_FUSION")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->fusion = v; }
     if (const char* e = getenv("VXRT_SHADE_THREADS")) {
         const int v = atoi(e);
         if (v == 64 || v == 128 || v == 256) c->shade_threads = v;
@@ -908,7 +911,9 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         c->launches++;
     }
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    const bool sweep = c->l2_prefetch == 1 || (c->l2_prefetch == 2 && c->map.nlocal <= 12000);
+    // auto: small shares whose primary pass reads the reference-layout grid (with the traversal grid its long rays no longer wait
+    // for a new line on every step, and the sweep costs more than it returns: 1/8 of a 4K frame 0.190 -> 0.184 ms without it)
+    const bool sweep = c->l2_prefetch == 1 || (c->l2_prefetch == 2 && c->map.nlocal <= 12000 && !use_trav_primary(c));
     if (sweep && (size_t)c->nvox * 4 <= (size_t)120 << 20) {              // only grids that fit the 126 MB L2
         // rows a ray can read: up to 7 above the highest solid row (beyond that the culling ends the ray), all rows otherwise
         int ytop = c->cfg.grid_h;
@@ -981,11 +986,25 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         } while (0)
         // overlap (whole-frame launches of the lit view only): nothing may be queued between the two passes, so the event that
         // separates their times and the refresh of the primary launch order move behind the shade pass
-        const bool overlap = nbands == 1 && c->frame.view_depth_field != 1 &&
+        const bool fused = nbands == 1 && (c->fusion == 1 || (c->fusion == 2 && c->map.nlocal <= 12000));
+        const bool overlap = !fused && nbands == 1 && c->frame.view_depth_field != 1 &&
                              (c->overlap == 1 || (c->overlap == 2 && c->map.nlocal <= 12000));
         o.overlap = overlap ? 1 : 0;
         o.tile_ready = c->d_tile_ready; o.overlap_err = c->d_overlap_err;
         o.frame_seq = ++c->frame_seq;
+        if (fused) {
+            // one kernel per frame: each block traces its tile's primary rays and then shades its own hits (kernels.cuh frame_kernel)
+            VXRT_LAUNCH(frame_kernel, count_primary, trav_primary, grid, block, false);
+            CUDA_TRY(cudaGetLastError());
+            c->launches++;
+            CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));          // (one kernel: ms_primary reads as the whole frame, ms_shadow as 0)
+            if (o.tile_cost && c->map.nlocal >= 64 && (c->order_frame < 2 || (c->order_frame % 8) == 0)) {
+                tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_tile_cost, c->d_tile_order, c->map.nlocal);
+                CUDA_TRY(cudaGetLastError());
+                c->launches++;
+                c->have_tile_order = true;
+            }
+        } else {
         VXRT_LAUNCH(primary_kernel, count_primary, trav_primary, grid, block, false);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
@@ -1020,6 +1039,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
                 c->order_shade_threads = c->shade_threads;
             }
         }
+        }   // two passes
         if (host_dst) {
             size_t off, bytes;
             if (c->cfg.world == 1) {
@@ -1092,6 +1112,14 @@ extern "C" int vxrt_download_traversal(vxrt_ctx* c, int32_t* out, size_t count) 
     if (!out || count != c->nvox) return fail(VXRT_ERR_INVALID, "download_traversal: count must equal grid_w*grid_h*grid_d");
     CUDA_TRY(cudaMemcpyAsync(out, c->d_trav, count * 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return VXRT_OK;
+}
+
+extern "C" int vxrt_set_fusion(vxrt_ctx* c, int mode) {
+    if (!c) return fail(VXRT_ERR_INVALID, "null context");
+    if (mode < 0 || mode > 2) return fail(VXRT_ERR_INVALID, "set_fusion: 0 two passes, 1 fused, 2 auto");
+    if (mode != c->fusion) { c->have_tile_order = false; c->have_shade_order = false; c->order_frame = 0; }   // block times mean something else now
+    c->fusion = mode;
     return VXRT_OK;
 }
 
