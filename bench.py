@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--e2e-path", default="auto", choices=["auto", "p2p", "host"],
                     help="N > 1, how the frame reaches rank 0's host memory: p2p = peer stores over NVLink + one read-back on rank 0; "
                          "host = every rank's kernels store into one shared page-locked host frame (auto: host from 4 GPUs on)")
+    ap.add_argument("--e2e-host-stores", action="store_true",
+                    help="host-frame e2e path: kernels store pixels into the host frame themselves (round 1's form) instead of the strip DMA")
     ap.add_argument("--partition", default="tiles", choices=["tiles", "frames"],
                     help="N > 1: 'tiles' (default, BASELINE's split) = every GPU renders its tiles of the SAME frame (strong scaling, "
                          "shorter frame latency); 'frames' = every GPU renders whole frames of its own (frame f on rank f %% N, no "
@@ -208,9 +210,11 @@ def run_b200(args):
         gathered = torch.empty(world * local_bytes, dtype=torch.uint8, device="cuda")
         final = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
         # zero-copy view of the renderer's device output buffer as a torch tensor
-        class _Buf:
-            __cuda_array_interface__ = {"shape": (local_bytes,), "typestr": "|u1", "data": (ren.device_rgba8_ptr(), False), "version": 3}
-        local_t = torch.as_tensor(_Buf(), device="cuda")
+        def bind_local():
+            class _Buf:
+                __cuda_array_interface__ = {"shape": (local_bytes,), "typestr": "|u1", "data": (ren.device_rgba8_ptr(), False), "version": 3}
+            return torch.as_tensor(_Buf(), device="cuda")
+        local_t = bind_local()
 
     def step_device():
         """one frame with inputs resident: kernels (+ gather + un-tile for N > 1) on the renderer's stream"""
@@ -223,9 +227,10 @@ def run_b200(args):
                     ren.p2pReleaseFrame()
         elif world > 1:
             with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(gathered, local_t)
+                dist.all_gather_into_tensor(gathered, nccl_state["local_t"])
             ren.assembleTiles(gathered.data_ptr(), final.data_ptr())
 
+    nccl_state = {"local_t": local_t}
     p2p_state = {"ptr": 0, "hold": False}
 
     edits_dev = edit_cmd = None
@@ -296,7 +301,9 @@ def run_b200(args):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     kern_ms_source = "CUDA events inside vxrt_render, frames of the timed region"
-    if frame.view_depth_field != 1 and max(kern_ms["shade"]) == 0.0:
+    fused_ms = None
+    if frame.view_depth_field != 1 and ren.frameWasFused():
+        fused_ms = statistics.mean(kern_ms["primary"]) + statistics.mean(kern_ms["shade"])     # the one kernel of the timed frames
         # the two passes are ONE kernel in this configuration (vxrt_set_fusion, auto): their separate durations come from the same
         # frames rendered once more as two kernels
         kern_ms = {"primary": [], "shade": []}
@@ -423,6 +430,11 @@ def run_b200(args):
             for h in hfs:
                 h.close()
             return False
+        # tile-row partition for this path: a rank's pixels are 8-row strips of the raster, rendered into a local buffer and moved into
+        # the shared host frame by one strided DMA per frame (vxrt_set_partition); --e2e-host-stores keeps the kernels' own stores
+        strips = not args.e2e_host_stores
+        if strips:
+            ren.setPartition(1)
         seq = [0, 0]
 
         def run(nframes, flush):
@@ -440,7 +452,7 @@ def run_b200(args):
             if rank == 0 and pending is not None:
                 hfs[pending[0]].wait(world, pending[1]); hfs[pending[0]].release(pending[1])
             ren.sync()
-        run(4, False)
+        run(12, False)
         if rank == 0:                                                 # the frame that arrived is the frame
             check = np.array(hfs[1].pixels(), copy=True)
         barrier()
@@ -451,11 +463,19 @@ def run_b200(args):
         barrier()
         # the frame that arrived in the shared host frame == the frame the exchange path delivered (sync loop above)
         e2e_state["frame_check"] = bool(np.array_equal(check, final_host.numpy())) if rank == 0 else True
-        e2e_state["api"] = ("every rank: vxrt_render_to_host_frame (host frame params in; its kernels store its tiles' pixels straight into one "
-                            "shared page-locked host frame over its own PCIe link, no exchange); rank 0: vxrt_host_frame_wait on every rank's "
+        e2e_state["api"] = ("every rank: vxrt_render_to_host_frame (host frame params in; " +
+                            ("tile-row partition: the rank renders its 8-row strips into a local buffer and ONE strided DMA per frame moves them "
+                             "into the shared page-locked host frame over its own PCIe link, overlapped with the next frame's kernels" if strips else
+                             "its kernels store its tiles' pixels straight into one shared page-locked host frame over its own PCIe link") +
+                            ", no exchange); rank 0: vxrt_host_frame_wait on every rank's "
                             "completion flag, overlapped with the next frame (two host frames alternate); wall clock / K, max over ranks")
         for h in hfs:
             h.close()
+        if strips:
+            ren.sync()
+            ren.setPartition(0)                                       # (re-allocates the local frame: re-bind the all-gather's source)
+            if not use_p2p:
+                nccl_state["local_t"] = bind_local()
         return True
 
     # (b) pipelined (N = 1): the same call in its queued form -- every step still passes its frame parameters in and
@@ -547,6 +567,8 @@ def run_b200(args):
         bytes_primary_ref, bytes_shade_ref = alg_bytes(st)
         dom = "shade_kernel" if shade_ms >= prim_ms else "primary_kernel"
         dom_ms, dom_bytes, dom_bytes_ref = (shade_ms, bytes_shade, bytes_shade_ref) if dom == "shade_kernel" else (prim_ms, bytes_primary, bytes_primary_ref)
+        if fused_ms is not None:                                  # the timed frames run ONE kernel (primary rays + lighting per tile)
+            dom, dom_ms, dom_bytes, dom_bytes_ref = "frame_kernel", fused_ms, bytes_primary + bytes_shade, bytes_primary_ref + bytes_shade_ref
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         achieved_ref = dom_bytes_ref / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         # ncu capture of this workload's kernels committed under profiles/ (scripts/ncu_summary.py): DRAM traffic per launch and the
@@ -556,6 +578,8 @@ def run_b200(args):
             try:
                 prof = json.load(open(os.path.join(ROOT, "profiles", prof_name)))
                 if prof.get("workload") == args.workload and world == 1:
+                    if dom not in prof["kernels"]:
+                        continue
                     kk = prof["kernels"][dom]
                     traffic = int(kk["dram_bytes_read"] + kk["dram_bytes_write"])
                     it_exec = (st_exec["fetches"] - st_exec["fetches_primary"]) if dom == "shade_kernel" else st_exec["fetches_primary"]
@@ -579,6 +603,10 @@ def run_b200(args):
                     "note": "HBM bookkeeping figure: algorithmic bytes (4 B x castRay iterations the kernel executes + colour read + RGBA8 store, rank 0's "
                             "tiles) / the kernel's CUDA-event time / measured copy peak.  The gathers are served by L1/L2 (DRAM traffic is a few % of the "
                             "algorithmic bytes): the binding resource is instruction issue, reported in 'issue' from the committed ncu capture",
+                    **({"frame_kernel": {"ms": round(fused_ms, 4), "alg_bytes": int(bytes_primary + bytes_shade),
+                                         "alg_bytes_reference_iterations": int(bytes_primary_ref + bytes_shade_ref),
+                                         "what": "the timed frames: one fused kernel per frame (vxrt_set_fusion auto for this share); 'kernels' below = the "
+                                                 "same frames rendered again as two kernels"}} if fused_ms is not None else {}),
                     "kernels": {"primary_kernel": {"ms": round(prim_ms, 4), "alg_bytes": int(bytes_primary), "alg_bytes_reference_iterations": int(bytes_primary_ref)},
                                 "shade_kernel": {"ms": round(shade_ms, 4), "alg_bytes": int(bytes_shade), "alg_bytes_reference_iterations": int(bytes_shade_ref)}}}
         result = {
@@ -639,6 +667,7 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+        nccl_state.clear()
         del gathered, final, local_t
     del flush, final_host, edits_dev, edit_cmd
     p2p_err = ren.p2pError() if use_p2p else 0

@@ -206,6 +206,15 @@ int vxrt_set_overlap(vxrt_ctx* ctx, int mode);
    blocks per SM) have the higher throughput.  Same pixels.  While fused, vxrt_get_stats cannot separate the passes
    (ms_primary = whole frame, ms_shadow = 0), and vxrt_set_overlap has no effect. */
 int vxrt_set_fusion(vxrt_ctx* ctx, int mode);
+/* Which image tiles a context of a multi-GPU split renders (all ranks must choose the same): 0 (default) tile t belongs to rank
+   t % world; 1 whole TILE ROWS are the interleaved unit -- tile row r belongs to rank r % world -- so that a rank's pixels are
+   contiguous 8-row strips of the raster frame.  With 1, vxrt_render_to_host_frame renders into a local strip buffer and moves the
+   strips into the shared host frame with ONE strided DMA on the copy stream (a DMA fills a PCIe link; stores from kernels reach
+   about 40 % of it), overlapped with the next frame; local buffers / the all-gather layout become [local strip][8][width].
+   Re-allocates the per-frame buffers.  Same pixels. */
+int vxrt_set_partition(vxrt_ctx* ctx, int mode);
+/* 1 when the last vxrt_render ran as one fused kernel (see vxrt_set_fusion), else 0. */
+int vxrt_frame_was_fused(vxrt_ctx* ctx);
 /* mode 0 (default) = the production kernels: no per-iteration counter, rays that cannot change a pixel are not traced
    (vxrt_set_culling); vxrt_get_stats then reads rays_local / fetches / rays_dark as 0 while hit_pixels, rays_primary,
    rays_global and the timings stay valid.  mode 1: every vxrt_render runs the counted kernel variants by the REFERENCE's

@@ -131,6 +131,30 @@ def main():
         hfs[1].release(3)
     ren.sync()
     dist.barrier()
+    # the same with the tile-row partition: every rank renders its 8-row strips into a local buffer, one strided DMA per frame
+    # moves them into the shared host frame (sequence numbers continue); ren2 (peer-memory context) renders a peer frame in that
+    # partition too
+    ren.setPartition(1)
+    strips_ok = True
+    for k in range(6, 12):
+        ren.renderToHostFrame(frame, hfs[k & 1], k // 2 + 1)
+        if rank == 0 and k >= 7:
+            j = k - 1
+            hfs[j & 1].wait(world, j // 2 + 1)
+            strips_ok &= bool(np.array_equal(hfs[j & 1].pixels(), got_edit))
+            hfs[j & 1].release(j // 2 + 1)
+    if rank == 0:
+        hfs[1].wait(world, 6)
+        strips_ok &= bool(np.array_equal(hfs[1].pixels(), got_edit))
+        hfs[1].release(6)
+    ren.sync()
+    dist.barrier()
+    ren.setPartition(0)
+    ren2.setPartition(1)
+    got_rows_p2p = render_frame_p2p(3)
+    ren2.setPartition(0)
+    if rank == 0:
+        strips_ok &= bool(np.array_equal(got_rows_p2p, got_edit_p2p))
     for h in hfs:
         h.close()
     p2p_err = ren2.p2pError()
@@ -163,6 +187,8 @@ def main():
         print("pipelined peer-memory read-back frames intact:", readback_ok)
         ok &= host_ok
         print("frames stored straight into the shared host frame vs gathered frame:", host_ok)
+        ok &= strips_ok
+        print("tile-row partition: strips moved into the shared host frame by DMA, and the peer-memory frame, equal the gathered frame:", strips_ok)
         ok &= all(f == o.fnv(level) for f in fnvs)
         print("replica fingerprints equal oracle:", all(f == o.fnv(level) for f in fnvs), ["%016x" % f for f in fnvs])
         want_trav, bad = o.trav_build(level, (512, 96, 512))

@@ -492,10 +492,13 @@ def test_update_partial_geometry_semantics(vx, oracle, default_level):
 
 
 # ---- tile partition on one GPU -------------------------------------------------------------------
+@pytest.mark.parametrize("rows", [False, True], ids=["tiles", "tile_rows"])
 @pytest.mark.parametrize("world", [2, 3, 8])
-def test_tile_partition_reassembles_the_frame(vx, default_level, world):
+def test_tile_partition_reassembles_the_frame(vx, default_level, world, rows):
+    """both partitions (vxrt_set_partition): tile t -> rank t % world, and whole tile rows -> rank row % world (a rank's local
+    buffer is then its 8-row strips); 416x236: the last tile row is cut by the frame's edge"""
     import torch
-    W, H = 416, 240
+    W, H = 416, 236
     fr = to_vx_frame(vx, gc.frame_cases(W, H)["C3ii_pitched"])
     with vx.Renderer(grid=gc.DIMS, width=W, height=H) as full:
         full.updateGeometry(default_level)
@@ -506,6 +509,7 @@ def test_tile_partition_reassembles_the_frame(vx, default_level, world):
     for rank in range(world):
         with vx.Renderer(grid=gc.DIMS, width=W, height=H, rank=rank, world=world) as r:
             r.updateGeometry(default_level)
+            r.setPartition(1 if rows else 0)
             r.setStats(True)
             parts.append(r.renderFrameHost(fr))
             st = r.stats()
@@ -515,9 +519,10 @@ def test_tile_partition_reassembles_the_frame(vx, default_level, world):
                 keep = r
                 gathered_host = None
     gathered = np.stack(parts)
-    assert np.array_equal(vx.tiles.assemble(gathered, W, H), want)
+    assert np.array_equal(vx.tiles.assemble(gathered, W, H, rows=rows), want)
     assert all(tot[k] == st_full[k] for k in tot)
     with vx.Renderer(grid=gc.DIMS, width=W, height=H, rank=0, world=world) as r:
+        r.setPartition(1 if rows else 0)
         g = torch.from_numpy(gathered).cuda()
         dst = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
         torch.cuda.synchronize()
@@ -582,11 +587,13 @@ def test_peer_memory_frame_target_protocol_on_one_gpu(vx, oracle, default_level)
             r.close()
 
 
-def test_host_frames_on_one_gpu(vx, oracle, default_level):
+@pytest.mark.parametrize("rows", [False, True], ids=["kernel_stores", "strip_dma"])
+def test_host_frames_on_one_gpu(vx, oracle, default_level, rows):
     """frames straight to host memory: three 'ranks' on one device store their tiles' pixels into one raster in shared
     page-locked memory (one handle created, one opened -- the way a second process maps it); completion flags, the
-    release back-pressure and two alternating host frames"""
-    W, H, world = 416, 240, 3
+    release back-pressure and two alternating host frames.  strip_dma: the tile-row partition, where a rank renders its 8-row
+    strips into a local buffer and one strided DMA per frame moves them into the host frame (236 rows: the last strip is cut)"""
+    W, H, world = 416, (236 if rows else 240), 3
     tag = "/vxrt_test_%d" % os.getpid()
     ctxs = [vx.Renderer(grid=gc.DIMS, width=W, height=H, rank=r, world=world) for r in range(world)]
     created = [vx.HostFrame(tag + "_a", W, H, create=True), vx.HostFrame(tag + "_b", W, H, create=True)]
@@ -598,6 +605,7 @@ def test_host_frames_on_one_gpu(vx, oracle, default_level):
             vx.HostFrame(tag + "_a", W + 32, H, create=False)
         for r in ctxs:
             r.updateGeometry(default_level)
+            r.setPartition(1 if rows else 0)
             r.setStats(False)
         names = ["C3ii_pitched", "C2", "C3i", "sparse_lights", "C1", "C2"]
         cases = gc.frame_cases(W, H)

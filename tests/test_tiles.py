@@ -40,6 +40,25 @@ def test_extract_assemble_round_trip(vx, size, world):
     assert np.array_equal(t.assemble(gathered, w, h), frame)
 
 
+@pytest.mark.parametrize("size", [(100, 37), (256, 64), (3840, 2160), (33, 9)])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_tile_row_partition(vx, size, world):
+    """vxrt_set_partition 1: tile rows interleaved, a rank's buffer = its 8-row strips, raster inside"""
+    t = vx.tiles
+    w, h = size
+    tx, ty, n = t.tile_counts(w, h)
+    allt = np.concatenate([t.tiles_of_rank(w, h, r, world, rows=True) for r in range(world)])
+    assert sorted(allt.tolist()) == list(range(n))
+    assert all(len(t.tiles_of_rank(w, h, r, world, rows=True)) <= t.local_tiles(w, h, world, rows=True) for r in range(world))
+    owner = t.pixel_owner(w, h, world, rows=True)
+    assert all((owner[y] == owner[y, 0]).all() for y in range(h))           # whole rows
+    if w * h <= 256 * 64:
+        frame = np.random.RandomState(2).randint(0, 256, size=(h, w, 4)).astype(np.uint8)
+        gathered = np.stack([t.extract_local(frame, r, world, rows=True) for r in range(world)])
+        assert gathered.shape[1] == t.local_tiles(w, h, world, rows=True) * 256
+        assert np.array_equal(t.assemble(gathered, w, h, rows=True), frame)
+
+
 def _gloo_worker(rank, world, port, level_path, tmpdir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

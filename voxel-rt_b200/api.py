@@ -87,6 +87,8 @@ _SIGNATURES = {
     "vxrt_set_tile_ordering": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_fusion": (C.c_int, [C.c_void_p, C.c_int]),
+    "vxrt_frame_was_fused": (C.c_int, [C.c_void_p]),
+    "vxrt_set_partition": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_render_frame_host": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p]),
     "vxrt_submit_frame_host": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p]),
@@ -391,6 +393,14 @@ class Renderer:
     def setFusion(self, mode):
         """0 two kernels per frame, 1 one fused kernel (a block traces its tile's primary rays, then shades its own hits), 2 auto"""
         self._check(self.lib.vxrt_set_fusion(self._h, int(mode)))
+
+    def setPartition(self, mode):
+        """0 tile t -> rank t % world (default), 1 tile row r -> rank r % world (a rank's pixels are 8-row strips: one strided DMA per frame)"""
+        self._check(self.lib.vxrt_set_partition(self._h, int(mode)))
+
+    def frameWasFused(self):
+        """the last draw() ran as one fused kernel (setFusion)"""
+        return bool(self.lib.vxrt_frame_was_fused(self._h))
 
     def setOverlap(self, mode):
         """0 off, 1 on, 2 auto (default): the shade pass starts inside the primary pass's tail (programmatic dependent launch)"""

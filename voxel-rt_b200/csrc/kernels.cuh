@@ -31,7 +31,14 @@ struct TileMap {
     int tx, ty, ntiles;                 // tiles per row / column / total
     int rank, world, nlocal;            // this context renders tiles t = j*world + rank, j in [0,nlocal)
     int tile_base;                      // first local tile of this launch (frames can be rendered in bands of tile rows)
+    int rows;                           // 1: whole TILE ROWS are the interleaved unit (vxrt_set_partition): tile row r belongs to rank r % world,
+                                        // local tile j = (local row j / tx, column j % tx); a rank's pixels are then contiguous 8-row strips
+                                        // of the raster frame, which one strided DMA moves to a host frame
 };
+// global tile of local tile j (>= ntiles: padding)
+__host__ __device__ __forceinline__ int tile_of(const TileMap& m, int j) {
+    return m.rows ? ((j / m.tx) * m.world + m.rank) * m.tx + (j % m.tx) : j * m.world + m.rank;
+}
 
 struct Counters {
     unsigned int hit_count;
@@ -60,6 +67,10 @@ struct Outputs {
     uint32_t frame_seq;
     int overlap;
     int* overlap_err;                   // set when a shade block gave up waiting (bounded spin)
+    // peer-memory frames (programmatic dependent launch): the first render kernel of a frame is launched while p2p_begin_kernel still
+    // waits for the owner (pdl_wait: griddepcontrol.wait before this kernel's first global write); the last one lets the kernel that
+    // publishes the rank's completion flag become resident early (pdl_trigger)
+    int pdl_wait, pdl_trigger;
     int32_t* dbg_hit;                   // optional (VXRT_FLAG_DEBUG_OUTPUTS), raster layout
     uint16_t* dbg_steps;
     uint32_t* dbg_occl;
@@ -68,6 +79,7 @@ struct Outputs {
 
 __device__ __forceinline__ uint32_t out_index_of(const TileMap& m, int raster, int px, int py) {
     if (raster) return (uint32_t)(py * m.width + px);
+    if (m.rows) return (uint32_t)((((py / TILE_H) / m.world) * TILE_H + (py % TILE_H)) * m.width + px);   // this rank's strips, raster inside
     const int t = (py / TILE_H) * m.tx + (px / TILE_W);
     const int local = t / m.world;
     return (uint32_t)(local * TILE_PIX + (py % TILE_H) * TILE_W + (px % TILE_W));
@@ -83,7 +95,7 @@ __device__ __forceinline__ uint32_t out_index_of(const TileMap& m, int raster, i
 template <bool COUNT, class Grid, bool TRAV>
 __device__ __forceinline__ bool primary_pixel(const Grid& g, const FrameParams& f, const TileMap& m, const Outputs& o, int local_tile,
                                               int warp, int lane, RayHit& r, uint32_t& pid) {
-    const int t = local_tile * m.world + m.rank;                    // global tile
+    const int t = tile_of(m, local_tile);                           // global tile
     const int lx = (warp & 3) * 8 + (lane & 7), ly = (warp >> 2) * 4 + (lane >> 3);
     const int px = (t % m.tx) * TILE_W + lx, py = (t / m.tx) * TILE_H + ly;
     const bool valid = (t < m.ntiles) && (px < m.width) && (py < m.height);
@@ -102,6 +114,7 @@ __device__ __forceinline__ bool primary_pixel(const Grid& g, const FrameParams& 
         const float ry = __fadd_rn(__fadd_rn(__fmul_rn(M[1], dxn), __fmul_rn(M[5], dyn)), __fadd_rn(__fmul_rn(M[9], dzn), __fmul_rn(M[13], 0.0f)));
         const float rz = __fadd_rn(__fadd_rn(__fmul_rn(M[2], dxn), __fmul_rn(M[6], dyn)), __fadd_rn(__fmul_rn(M[10], dzn), __fmul_rn(M[14], 0.0f)));
         r = cast_ray<COUNT, false, true, Grid, TRAV>(g, f.cam_pos[0], f.cam_pos[1], f.cam_pos[2], rx, ry, rz, VXRT_RENDER_DIST);   // :139
+        if (o.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");   // nothing is written before the kernel ahead has completed
         if (f.view_depth_field == 1) {                               // :143-145
             const float grey = __fdiv_rn((float)r.steps, 100.0f);
             o.rgba8[out_index_of(m, o.raster, px, py)] = pack_rgba8(grey, grey, grey, 1.0f);
@@ -131,7 +144,7 @@ __global__ void __launch_bounds__(256, 6) primary_kernel(Grid g, const __grid_co
     if (tid == 0) s_fetches = 0ull;
     // overlap: the shade pass (launched with programmatic stream serialization) may be scheduled as soon as every block of this
     // grid has started, i.e. into the SM capacity this pass's tail leaves idle
-    if (o.overlap) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (o.overlap || o.pdl_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const long long t_start = clock64();
     // blocks are handed out in launch order: with a tile order from the previous frame the slowest tiles start first,
     // which shortens the kernel's tail (it matters once a GPU renders only 1/4 or 1/8 of the frame)
@@ -139,6 +152,7 @@ __global__ void __launch_bounds__(256, 6) primary_kernel(Grid g, const __grid_co
     RayHit r;
     uint32_t pid;
     const bool hit = primary_pixel<COUNT, Grid, TRAV>(g, f, m, o, local_tile, warp, lane, r, pid);
+    if (o.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");       // (threads without a pixel have not waited yet)
     // ---- hit compaction into the tile's 256 slots: warp ballot -> block prefix (no global ordering: the shade pass
     //      schedules tiles by its own cost feedback) ---------------------------------------------------------------
     const unsigned ballot = __ballot_sync(0xffffffffu, hit);
@@ -330,6 +344,7 @@ __global__ void __launch_bounds__(256, 5) shade_kernel(Grid g, const __grid_cons
     __shared__ LightList s_lights;
     __shared__ unsigned long long s_fetches, s_local;
     const int tid = threadIdx.x, lane = tid & 31;
+    if (o.pdl_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // a shade unit = blockDim.x consecutive slots of one tile; units are launched slowest-first (previous frame's times)
     const long long t_start = clock64();
     const int unit = o.shade_order ? (int)o.shade_order[blockIdx.x] : (int)blockIdx.x + o.shade_unit_base;
@@ -381,6 +396,7 @@ __global__ void __launch_bounds__(256, 5) frame_kernel(Grid g, const __grid_cons
     __shared__ unsigned int s_total;
     __shared__ unsigned long long s_fetches, s_local, s_fetches_primary;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (o.pdl_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const long long t_start = clock64();
     const int local_tile = o.tile_order ? (int)o.tile_order[blockIdx.x] : (int)blockIdx.x + m.tile_base;
     compact_lights(f, s_lights, tid, lane);
@@ -388,6 +404,7 @@ __global__ void __launch_bounds__(256, 5) frame_kernel(Grid g, const __grid_cons
     RayHit r;
     uint32_t pid;
     const bool hit = primary_pixel<COUNT, Grid, TRAV>(g, f, m, o, local_tile, warp, lane, r, pid);
+    if (o.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");       // (threads without a pixel have not waited yet)
     const unsigned ballot = __ballot_sync(0xffffffffu, hit);
     const unsigned wfetch = __reduce_add_sync(0xffffffffu, (unsigned)r.steps);
     if (lane == 0) s_warp_hits[warp] = __popc(ballot);
@@ -595,7 +612,8 @@ __global__ void division_selftest_kernel(unsigned long long n, unsigned long lon
 struct P2PShared {
     unsigned long long consumed;        // frames the owner has finished reading (written by the owner)
     unsigned long long width, height, world;   // the owner's frame extents and world size (importers must match them)
-    unsigned long long pad0[12];
+    unsigned long long owner_device;    // 1 + (PCI domain << 16 | bus << 8 | device) of the owner's GPU (0: unknown)
+    unsigned long long pad0[11];
     unsigned long long done[16 * 16];   // done[16*r] = frames rank r has completely written (stride 128 B)
 };
 
@@ -622,8 +640,19 @@ __device__ __forceinline__ bool spin_until(const unsigned long long* p, unsigned
 __global__ void p2p_wait_consumed_kernel(const P2PShared* sh, unsigned long long seq, int* err) {
     if (seq >= 2 && !spin_until(&sh->consumed, seq - 1)) *err = 1;
 }
-// all ranks, after rendering frame `seq`
+// The same wait as the head of a frame whose first render kernel is launched with programmatic stream serialization: that kernel's
+// blocks start at once (launch_dependents below) and trace their primary rays while this one still waits; they execute
+// griddepcontrol.wait -- this grid completed, its writes visible -- before their first global write.  Also zeroes the frame's
+// counters (instead of a memset node in the stream).  One block of 64 threads.
+__global__ void __launch_bounds__(64) p2p_begin_kernel(const P2PShared* sh, unsigned long long seq, int* err, unsigned int* counters, int nwords) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) counters[i] = 0u;
+    if (threadIdx.x == 0 && seq >= 2 && !spin_until(&sh->consumed, seq - 1)) *err = 1;
+}
+// all ranks, after rendering frame `seq` (griddepcontrol.wait: no-op unless launched with programmatic stream serialization, where
+// it returns once the render kernel ahead has completed and its stores -- the pixels in the owner's frame -- are performed)
 __global__ void p2p_signal_done_kernel(P2PShared* sh, int rank, unsigned long long seq) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __threadfence_system();
     st_release_sys(&sh->done[16 * rank], seq + 1);
 }
@@ -650,6 +679,11 @@ __global__ void assemble_kernel(const uint32_t* __restrict__ gathered, uint32_t*
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= m.width * m.height) return;
     const int px = p % m.width, py = p / m.width;
+    if (m.rows) {                                                   // [world][local strip][8][width]
+        const int row = py / TILE_H, rank = row % m.world;
+        dst[p] = gathered[(size_t)rank * m.nlocal * TILE_PIX + (size_t)((row / m.world) * TILE_H + (py % TILE_H)) * m.width + px];
+        return;
+    }
     const int t = (py / TILE_H) * m.tx + (px / TILE_W);
     const int rank = t % m.world, local = t / m.world;
     dst[p] = gathered[((size_t)rank * m.nlocal + local) * TILE_PIX + (py % TILE_H) * TILE_W + (px % TILE_W)];

@@ -92,6 +92,8 @@ struct vxrt_ctx {
     uint32_t* d_tile_ready = nullptr;   // per local tile: frame_seq of the last primary pass that finished it
     int* d_overlap_err = nullptr;
     uint32_t frame_seq = 0;
+    bool last_fused = false;            // the last frame ran as one fused kernel
+    bool row_partition = false;         // vxrt_set_partition: whole tile rows are the interleaved unit
     bool use_culling = true;
     int l2_prefetch = 2;                // vxrt_set_l2_prefetch: 0 off, 1 on, 2 auto (on when this context renders <= 12,000 tiles)
     int shade_threads = 128;            // threads per shade block (VXRT_SHADE_THREADS: 64 / 128 / 256; 128 measured best)
@@ -116,6 +118,8 @@ struct vxrt_ctx {
     size_t p2p_frame_bytes = 0;
     unsigned long long p2p_seq = 0;     // frames rendered into the target so far
     int* d_p2p_err = nullptr;
+    bool p2p_begin_overlap = false;     // the frame's first render kernel may start while p2p_begin_kernel waits (importers on another device only)
+    bool p2p_pdl = true;                // flag protocol chained with programmatic dependent launches (VXRT_P2P_PDL=0: separate plain launches)
     int stats_mode = 0;                 // vxrt_set_stats: 0 = production kernels (no per-iteration counters); 1 = counted variants, every ray
                                         // the reference casts is marched to its end (ray / fetch counts by the reference's casting rule);
                                         // 2 = counted variants that skip what the production kernels skip (counts of what is executed)
@@ -123,13 +127,14 @@ struct vxrt_ctx {
 };
 
 // ---- helpers -----------------------------------------------------------------------------------
-static TileMap make_map(int width, int height, int rank, int world) {
+static TileMap make_map(int width, int height, int rank, int world, bool rows) {
     TileMap m;
     m.width = width; m.height = height;
     m.tx = (width + TILE_W - 1) / TILE_W; m.ty = (height + TILE_H - 1) / TILE_H;
     m.ntiles = m.tx * m.ty;
     m.rank = rank; m.world = world;
-    m.nlocal = (m.ntiles + world - 1) / world;
+    m.rows = (rows && world > 1) ? 1 : 0;
+    m.nlocal = m.rows ? ((m.ty + world - 1) / world) * m.tx : (m.ntiles + world - 1) / world;
     m.tile_base = 0;
     return m;
 }
@@ -167,7 +172,7 @@ static void free_frame_buffers(vxrt_ctx* c) {
 
 static int alloc_frame_buffers(vxrt_ctx* c) {
     free_frame_buffers(c);
-    c->map = make_map(c->cfg.width, c->cfg.height, c->cfg.rank, c->cfg.world);
+    c->map = make_map(c->cfg.width, c->cfg.height, c->cfg.rank, c->cfg.world, c->row_partition);
     const size_t npix = (size_t)c->cfg.width * c->cfg.height;
     const size_t local_pix = (size_t)c->map.nlocal * TILE_PIX;
     c->out_pixels = (c->cfg.world == 1) ? npix : local_pix;
@@ -396,6 +401,7 @@ extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     if (const char* e = getenv("VXRT_TRAVERSAL")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->trav_mode = v; }
     if (const char* e = getenv("VXRT_OVERLAP")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->overlap = v; }
     if (const char* e = getenv("VXRT_FUSION")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->fusion = v; }
+    if (const char* e = getenv("VXRT_P2P_PDL")) c->p2p_pdl = atoi(e) != 0;
     if (const char* e = getenv("VXRT_SHADE_THREADS")) {
         const int v = atoi(e);
         if (v == 64 || v == 128 || v == 256) c->shade_threads = v;
@@ -873,8 +879,9 @@ extern "C" int vxrt_resize(vxrt_ctx* c, int width, int height) {                
 // Launches the frame's kernels in `nbands` bands of whole tile rows.  host_dst != nullptr: each band's pixels are
 // copied to host_dst (page-locked) on the copy stream as soon as the band's kernels finish, so the read-back of
 // band b overlaps the rendering of band b+1.
-static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* dev_out = nullptr, bool fence_main = true, bool raster_out = false) {
-    const bool p2p_frame = c->p2p && !raster_out;         // a host-frame render of a peer-memory context leaves the peer frame alone
+static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* dev_out = nullptr, bool fence_main = true, bool raster_out = false,
+                        bool local_out = false) {
+    const bool p2p_frame = c->p2p && !raster_out && !local_out;   // a host-frame render of a peer-memory context leaves the peer frame alone
     if (!dev_out) dev_out = c->d_rgba8;
     if (fence_main)                                       // synchronous paths: never overwrite a frame a pipelined copy still reads
         for (int slot = 0; slot < 2; slot++)
@@ -898,19 +905,36 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
     // bands: whole tile rows when this context owns the whole frame (raster rows stay contiguous), else tile ranges
     const int units = (c->cfg.world == 1) ? c->map.ty : c->map.nlocal;
     const int tiles_per_unit = (c->cfg.world == 1) ? c->map.tx : 1;
+    if (c->map.rows) nbands = 1;                          // (a rank's strips hold whole tile rows: no contiguous tile ranges to band over)
     if (nbands > units) nbands = units;
     if (nbands > MAX_BANDS) nbands = MAX_BANDS;
     if (nbands < 1) nbands = 1;
     c->launches = 0;
     c->bands_used = nbands;
-    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(Counters) * MAX_BANDS, c->stream));
-    if (p2p_frame) {
-        if (host_dst) return fail(VXRT_ERR_STATE, "render_frame_host is not available on a peer-memory context: use vxrt_p2p_wait_frame on the owner");
-        p2p_wait_consumed_kernel<<<1, 1, 0, c->stream>>>((const P2PShared*)c->p2p_base, c->p2p_seq, c->d_p2p_err);
+    // Peer-memory frames: the flag protocol rides on programmatic dependent launches, so that none of its kernels costs a launch
+    // gap on the frame's critical path -- p2p_begin_kernel (back-pressure wait + counter reset) runs WHILE the first render kernel
+    // traces its primary rays (that kernel executes griddepcontrol.wait before its first global write), and the kernel that
+    // publishes this rank's completion flag is resident before the last render kernel ends.  Nothing may be queued between the
+    // members of such a pair: the frame's events bracket the whole chain and the launch-order refreshes follow it.
+    const bool pdl_chain = p2p_frame && c->p2p_pdl;
+    if (p2p_frame && host_dst) return fail(VXRT_ERR_STATE, "render_frame_host is not available on a peer-memory context: use vxrt_p2p_wait_frame on the owner");
+    if (pdl_chain) {
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+        p2p_begin_kernel<<<1, 64, 0, c->stream>>>((const P2PShared*)c->p2p_base, c->p2p_seq, c->d_p2p_err, (unsigned int*)c->d_counters,
+                                                  (int)(sizeof(Counters) * MAX_BANDS / sizeof(unsigned int)));
         CUDA_TRY(cudaGetLastError());
         c->launches++;
+    } else {
+        CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, sizeof(Counters) * MAX_BANDS, c->stream));
+        if (p2p_frame) {
+            p2p_wait_consumed_kernel<<<1, 1, 0, c->stream>>>((const P2PShared*)c->p2p_base, c->p2p_seq, c->d_p2p_err);
+            CUDA_TRY(cudaGetLastError());
+            c->launches++;
+        }
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     }
-    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    bool pdl_first = pdl_chain && c->p2p_begin_overlap;    // the next render kernel is the first of the frame and may overlap the wait
+    bool refresh_tiles_later = false, refresh_shade_later = false, ev1_recorded = false;
     // auto: small shares whose primary pass reads the reference-layout grid (with the traversal grid its long rays no longer wait
     // for a new line on every step, and the sweep costs more than it returns: 1/8 of a 4K frame 0.190 -> 0.184 ms without it)
     const bool sweep = c->l2_prefetch == 1 || (c->l2_prefetch == 2 && c->map.nlocal <= 12000 && !use_trav_primary(c));
@@ -924,6 +948,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         l2_prefetch_kernel<<<148 * 8, 256, 0, c->stream>>>(trav_primary ? c->d_trav : c->d_vox, lines_per_slab, slab_ints, nlines, c->d_yrange ? c->d_yrange + 2 : nullptr);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
+        pdl_first = false;                                // (the sweep, a plain launch, already waited for p2p_begin_kernel)
     }
     // Banded read-back: the copy of a band overlaps the kernels of the bands after it, so the frame is in host memory
     // soonest when the cheapest bands render first (their copies hide behind the expensive ones) -- the order of the
@@ -992,27 +1017,39 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         o.overlap = overlap ? 1 : 0;
         o.tile_ready = c->d_tile_ready; o.overlap_err = c->d_overlap_err;
         o.frame_seq = ++c->frame_seq;
+        c->last_fused = fused;
+        o.pdl_wait = 0; o.pdl_trigger = 0;
+        const bool shade_follows = !fused && c->frame.view_depth_field != 1;
         if (fused) {
             // one kernel per frame: each block traces its tile's primary rays and then shades its own hits (kernels.cuh frame_kernel)
-            VXRT_LAUNCH(frame_kernel, count_primary, trav_primary, grid, block, false);
+            o.pdl_wait = pdl_first ? 1 : 0; o.pdl_trigger = pdl_chain ? 1 : 0;
+            VXRT_LAUNCH(frame_kernel, count_primary, trav_primary, grid, block, pdl_first);
             CUDA_TRY(cudaGetLastError());
             c->launches++;
-            CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));          // (one kernel: ms_primary reads as the whole frame, ms_shadow as 0)
+            pdl_first = false;
+            if (!pdl_chain) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));   // (one kernel: ms_primary reads as the whole frame, ms_shadow as 0)
             if (o.tile_cost && c->map.nlocal >= 64 && (c->order_frame < 2 || (c->order_frame % 8) == 0)) {
-                tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_tile_cost, c->d_tile_order, c->map.nlocal);
-                CUDA_TRY(cudaGetLastError());
-                c->launches++;
-                c->have_tile_order = true;
+                if (pdl_chain) refresh_tiles_later = true;
+                else {
+                    tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_tile_cost, c->d_tile_order, c->map.nlocal);
+                    CUDA_TRY(cudaGetLastError());
+                    c->launches++;
+                    c->have_tile_order = true;
+                }
             }
         } else {
-        VXRT_LAUNCH(primary_kernel, count_primary, trav_primary, grid, block, false);
+        o.pdl_wait = pdl_first ? 1 : 0; o.pdl_trigger = (pdl_chain && !shade_follows) ? 1 : 0;
+        VXRT_LAUNCH(primary_kernel, count_primary, trav_primary, grid, block, pdl_first);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
-        if (nbands == 1 && !overlap) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        pdl_first = false;
+        o.pdl_wait = 0; o.pdl_trigger = (pdl_chain && shade_follows) ? 1 : 0;
+        if (nbands == 1 && !overlap && !(pdl_chain && !shade_follows)) { CUDA_TRY(cudaEventRecord(c->ev[1], c->stream)); ev1_recorded = true; }
         // the launch orders are refreshed on the first two frames and then every 8th (block times are temporally
         // coherent; the one-block sort costs ~30 us at 4K)
         const bool refresh_order = c->order_frame < 2 || (c->order_frame % 8) == 0;
         auto refresh_tile_order = [&]() -> int {
+            if (pdl_chain) { refresh_tiles_later = o.tile_cost && c->map.nlocal >= 64 && refresh_order; return VXRT_OK; }
             if (o.tile_cost && c->map.nlocal >= 64 && refresh_order) {
                 tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_tile_cost, c->d_tile_order, c->map.nlocal);
                 CUDA_TRY(cudaGetLastError());
@@ -1029,9 +1066,11 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
             c->launches++;
             if (overlap) {
                 CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));      // (the passes overlap: ms_primary then reads as the whole frame, ms_shadow as 0)
+                ev1_recorded = true;
                 const int rc = refresh_tile_order(); if (rc != VXRT_OK) return rc;
             }
-            if (o.shade_cost && c->map.nlocal >= 64 && refresh_order) {
+            if (pdl_chain) refresh_shade_later = o.shade_cost && c->map.nlocal >= 64 && refresh_order;
+            else if (o.shade_cost && c->map.nlocal >= 64 && refresh_order) {
                 tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_shade_cost, c->d_shade_order, c->map.nlocal * upt);
                 CUDA_TRY(cudaGetLastError());
                 c->launches++;
@@ -1053,6 +1092,37 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
             CUDA_TRY(cudaMemcpyAsync(host_dst + off, (const uint8_t*)dev_out + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
         }
     }
+    if (pdl_chain) {
+        // the completion flag directly behind the last render kernel (resident before that kernel ends), then the events and the
+        // launch-order refreshes that had to stay out of the chain
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof lc);
+        lc.gridDim = dim3(1); lc.blockDim = dim3(1); lc.stream = c->stream;
+        cudaLaunchAttribute la[1];
+        la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        la[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = la; lc.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&lc, p2p_signal_done_kernel, (P2PShared*)c->p2p_base, (int)c->cfg.rank, c->p2p_seq));
+        c->launches++;
+        c->p2p_seq++;
+        if (!ev1_recorded) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));   // (one render kernel: ms_primary reads as the whole frame)
+        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        if (refresh_tiles_later) {
+            tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_tile_cost, c->d_tile_order, c->map.nlocal);
+            CUDA_TRY(cudaGetLastError());
+            c->launches++;
+            c->have_tile_order = true;
+        }
+        if (refresh_shade_later) {
+            const int upt = TILE_PIX / c->shade_threads;
+            tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_shade_cost, c->d_shade_order, c->map.nlocal * upt);
+            CUDA_TRY(cudaGetLastError());
+            c->launches++;
+            c->have_shade_order = true;
+            c->order_shade_threads = c->shade_threads;
+        }
+        if (nbands == 1 && c->use_tile_order) c->order_frame++;
+    } else {
     if (nbands != 1) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
     if (nbands == 1 && c->use_tile_order) c->order_frame++;
@@ -1061,6 +1131,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         CUDA_TRY(cudaGetLastError());
         c->launches++;
         c->p2p_seq++;
+    }
     }
     if (host_dst && fence_main) {                         // later work on the main stream must not overwrite pixels in flight
         CUDA_TRY(cudaEventRecord(c->ev_copy, c->copy_stream));
@@ -1122,6 +1193,18 @@ extern "C" int vxrt_set_fusion(vxrt_ctx* c, int mode) {
     c->fusion = mode;
     return VXRT_OK;
 }
+
+extern "C" int vxrt_set_partition(vxrt_ctx* c, int mode) {
+    CHECK_CTX(c);
+    if (mode != 0 && mode != 1) return fail(VXRT_ERR_INVALID, "set_partition: 0 tiles, 1 tile rows");
+    if ((mode == 1) == c->row_partition) return VXRT_OK;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    c->row_partition = mode == 1;
+    return alloc_frame_buffers(c);       // other local tiles: hit slots, launch orders and the local frame start over
+}
+
+extern "C" int vxrt_frame_was_fused(vxrt_ctx* c) { return (c && c->last_fused) ? 1 : 0; }
 
 extern "C" int vxrt_set_overlap(vxrt_ctx* c, int mode) {
     if (!c) return fail(VXRT_ERR_INVALID, "null context");
@@ -1250,7 +1333,7 @@ extern "C" int vxrt_get_stats(vxrt_ctx* c, vxrt_stats* out) {
     // pixels this context rendered (padding tiles and clipped pixels excluded)
     uint64_t pix = 0;
     for (int j = 0; j < c->map.nlocal; j++) {
-        const int t = j * c->map.world + c->map.rank;
+        const int t = tile_of(c->map, j);
         if (t >= c->map.ntiles) break;
         const int x0 = (t % c->map.tx) * TILE_W, y0 = (t / c->map.tx) * TILE_H;
         const int w = (c->map.width - x0 < TILE_W) ? c->map.width - x0 : TILE_W;
@@ -1359,6 +1442,12 @@ extern "C" void* vxrt_device_rgba8(vxrt_ctx* c) { return c ? (void*)c->d_rgba8 :
 extern "C" void* vxrt_stream(vxrt_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 // ---- peer-memory frame target ----------------------------------------------------------------------
+static unsigned long long pci_identity(int device) {
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, device) != cudaSuccess) { cudaGetLastError(); return 0ull; }
+    return 1ull + (((unsigned long long)pr.pciDomainID << 16) | ((unsigned long long)pr.pciBusID << 8) | (unsigned long long)pr.pciDeviceID);
+}
+
 extern "C" int vxrt_p2p_export(vxrt_ctx* c, uint8_t handle[64]) {
     CHECK_CTX(c);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1370,7 +1459,8 @@ extern "C" int vxrt_p2p_export(vxrt_ctx* c, uint8_t handle[64]) {
     CUDA_TRY(cudaMalloc(&c->p2p_base, total));
     CUDA_TRY(cudaMemset(c->p2p_base, 0, total));
     {   // header: what an importer's context must look like
-        const unsigned long long hdr[3] = {(unsigned long long)c->cfg.width, (unsigned long long)c->cfg.height, (unsigned long long)c->cfg.world};
+        const unsigned long long hdr[4] = {(unsigned long long)c->cfg.width, (unsigned long long)c->cfg.height, (unsigned long long)c->cfg.world,
+                                           pci_identity(c->cfg.device)};
         CUDA_TRY(cudaMemcpy(c->p2p_base + offsetof(P2PShared, width), hdr, sizeof hdr, cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaMalloc(&c->d_p2p_err, sizeof(int)));
@@ -1385,8 +1475,14 @@ extern "C" int vxrt_p2p_export(vxrt_ctx* c, uint8_t handle[64]) {
 // an importer stores into the owner's frame with ITS OWN extents and rank: both must be what the owner allocated for
 static int p2p_check_header(vxrt_ctx* c, const void* base) {
     if (c->cfg.world > 16 || c->cfg.rank >= 16) return fail(VXRT_ERR_INVALID, "peer-memory target supports up to 16 ranks");
-    unsigned long long hdr[3] = {0, 0, 0};
+    unsigned long long hdr[4] = {0, 0, 0, 0};
     CUDA_TRY(cudaMemcpy(hdr, (const uint8_t*)base + offsetof(P2PShared, width), sizeof hdr, cudaMemcpyDeviceToHost));
+    // The back-pressure wait may run WHILE this context's first render kernel already occupies the GPU (programmatic dependent
+    // launch) only if the owner's release cannot depend on this GPU: a kernel with undispatched blocks keeps the kernels of other
+    // streams from being dispatched, so on the owner's own device the release would wait behind it (a deadlock the bounded spin
+    // ends after 4 s).  Other device than the owner's: safe.
+    const unsigned long long mine = pci_identity(c->cfg.device);
+    c->p2p_begin_overlap = hdr[3] != 0 && mine != 0 && hdr[3] != mine;
     if (hdr[0] != (unsigned long long)c->cfg.width || hdr[1] != (unsigned long long)c->cfg.height || hdr[2] != (unsigned long long)c->cfg.world)
         return fail(VXRT_ERR_INVALID, "peer-memory target: the owner's frame is " + std::to_string(hdr[0]) + "x" + std::to_string(hdr[1]) + " for " +
                     std::to_string(hdr[2]) + " ranks, this context renders " + std::to_string(c->cfg.width) + "x" + std::to_string(c->cfg.height) +
@@ -1559,9 +1655,45 @@ extern "C" int vxrt_render_to_host_frame(vxrt_ctx* c, const vxrt_frame* f, vxrt_
     if (seq > 1 && !host_spin_until(&fl->released, seq - 1, 4000)) return fail(VXRT_ERR_STATE, "render_to_host_frame: the display rank did not release the previous frame (4 s)");
     void* dpix = nullptr;
     CUDA_TRY(cudaHostGetDevicePointer(&dpix, hf->base, 0));
+    unsigned long long* dflag = (unsigned long long*)((uint8_t*)dpix + ((uint8_t*)&fl->done[c->cfg.rank] - hf->base));
+    if (c->map.rows) {
+        // Tile-row partition (vxrt_set_partition 1): this rank's pixels are whole 8-row strips of the raster frame.  The kernels
+        // render them into a LOCAL strip buffer and ONE strided DMA (source pitch = a strip, destination pitch = world strips) moves
+        // them into the shared host frame on the copy stream -- a DMA fills a PCIe link, 128-byte stores from kernels reach about
+        // 40 % of it -- while the main stream already renders the next frame into the other local buffer.  The completion flag
+        // follows the copy in the copy stream.
+        if (!c->d_rgba8_alt) CUDA_TRY(cudaMalloc(&c->d_rgba8_alt, c->out_pixels * 4));
+        const int slot = (int)(c->submit_seq & 1);
+        if (c->slot_busy[slot]) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_slot[slot], 0));     // its previous copy still reads it
+        uint32_t* local = slot ? c->d_rgba8_alt : c->d_rgba8;
+        rc = render_bands(c, 1, nullptr, local, /*fence_main=*/false, /*raster_out=*/false, /*local_out=*/true);
+        if (rc != VXRT_OK) return rc;
+        CUDA_TRY(cudaEventRecord(c->ev_band[0], c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_band[0], 0));
+        const int W = c->cfg.width, H = c->cfg.height, world = c->cfg.world, rank = c->cfg.rank;
+        const size_t strip = (size_t)W * TILE_H * 4;
+        const int my_rows = (c->map.ty > rank) ? (c->map.ty - rank + world - 1) / world : 0;      // tile rows rank, rank + world, ...
+        if (my_rows > 0) {
+            const int last_row = rank + (my_rows - 1) * world;                                    // may be cut by the frame's lower edge
+            const int last_h = (H - last_row * TILE_H < TILE_H) ? H - last_row * TILE_H : TILE_H;
+            const int full = (last_h == TILE_H) ? my_rows : my_rows - 1;
+            uint8_t* dst0 = hf->base + (size_t)rank * strip;
+            if (full > 0)
+                CUDA_TRY(cudaMemcpy2DAsync(dst0, (size_t)world * strip, local, strip, strip, (size_t)full, cudaMemcpyDeviceToHost, c->copy_stream));
+            if (full < my_rows)
+                CUDA_TRY(cudaMemcpyAsync(dst0 + (size_t)full * world * strip, (const uint8_t*)local + (size_t)full * strip, (size_t)W * last_h * 4,
+                                         cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+        host_flag_kernel<<<1, 1, 0, c->copy_stream>>>(dflag, (unsigned long long)seq);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+        CUDA_TRY(cudaEventRecord(c->ev_slot[slot], c->copy_stream));
+        c->slot_busy[slot] = true;
+        c->submit_seq++;
+        return VXRT_OK;
+    }
     rc = render_bands(c, 1, nullptr, (uint32_t*)dpix, /*fence_main=*/true, /*raster_out=*/true);
     if (rc != VXRT_OK) return rc;
-    unsigned long long* dflag = (unsigned long long*)((uint8_t*)dpix + ((uint8_t*)&fl->done[c->cfg.rank] - hf->base));
     host_flag_kernel<<<1, 1, 0, c->stream>>>(dflag, (unsigned long long)seq);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
