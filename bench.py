@@ -9,7 +9,7 @@
 A "step" is one frame: the per-pixel path (primary DDA + shadow/light rays + shading) over every pixel of
 the frame.  Rays are counted by the REFERENCE's casting rule: W*H primary rays, one global-light
 ray per hit pixel, one local-light ray per (hit pixel, light) the reference shader would cast.
-N > 1: sort-first image-tile split (tile t -> rank t % N), grid replicated, one NCCL all-gather of the RGBA8
+N > 1: sort-first image-tile split (groups of N consecutive tiles dealt one to each rank, rotated per tile row), grid replicated, one NCCL all-gather of the RGBA8
 tiles per frame + an un-tile kernel on every rank; total work is fixed => "scaling": "strong".
 --partition frames (opt-in): whole frames are the sharded unit instead (frame f on rank f % N, nothing exchanged) => "weak".
 
@@ -197,6 +197,7 @@ def run_b200(args):
     stream = torch.cuda.ExternalStream(ren.stream_ptr(), device=torch.device("cuda", local_rank))
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
     local_bytes = ren.local_bytes()
+    gathered = final = local_t = None
     if use_p2p:
         handle = torch.zeros(64, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -204,7 +205,6 @@ def run_b200(args):
         dist.broadcast(handle, src=0)
         if rank != 0:
             ren.p2pImport(handle.cpu().numpy())
-        gathered = final = local_t = None
     elif world > 1:
         local_t = torch.empty(0)                                  # placeholder; real tensors below
         gathered = torch.empty(world * local_bytes, dtype=torch.uint8, device="cuda")
@@ -574,7 +574,7 @@ def run_b200(args):
         # ncu capture of this workload's kernels committed under profiles/ (scripts/ncu_summary.py): DRAM traffic per launch and the
         # issue-slot figures -- the resource that actually binds these kernels
         traffic, issue = None, None
-        for prof_name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        for prof_name in ("r2_ncu_traffic_%s.json" % args.workload, "r2_ncu_traffic.json", "r1_ncu_traffic.json"):
             try:
                 prof = json.load(open(os.path.join(ROOT, "profiles", prof_name)))
                 if prof.get("workload") == args.workload and world == 1:
@@ -614,7 +614,10 @@ def run_b200(args):
             "value_counts": "rays the timed kernels trace (primary + lit global + lit local); see value_reference_casting_rule / value_all_rays_marched",
             "value_reference_casting_rule": round(value_ref_rule, 2),
             "value_all_rays_marched": None,
-            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": round(ms_per_step, 4),
+            "ms_per_step_spread": {"min": round(min(step_ms), 4), "median": round(statistics.median(step_ms), 4), "max": round(max(step_ms), 4),
+                                   "of": "rank 0's per-frame CUDA-event times (ms_per_step is the max over ranks of their mean)"},
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (reference procedural default level, fnv1a64 %s; fixed camera)" % level_fnv,
             "config": {"workload": args.workload, "grid": list(grid), "width": W, "height": H, "local_lights": 16 if scene != "C1" else 0,
                        "setup": build_info,
@@ -627,7 +630,7 @@ def run_b200(args):
                        "counts": "rays_per_frame / rays_global / rays_local / voxel_fetches_per_frame follow the reference's casting rule (counted kernel "
                                  "variants, every ray marched to its end); rays_traced* / iterations_executed* are what the timed production kernels do; "
                                  "all summed over ranks",
-                       "partition": "sort-first 32x8 tiles, tile t -> rank t %% %d, grid replicated; frame exchange: %s" % (
+                       "partition": "sort-first 32x8 tiles, every %d consecutive tiles dealt one to each rank (rotated per tile row), grid replicated; frame exchange: %s" % (
                            world, "none (1 GPU)" if world == 1 else ("kernels store into rank 0's frame over NVLink peer memory, release/acquire flags" if use_p2p
                                                                      else "NCCL all-gather of RGBA8 tiles + un-tile kernel")),
                        "miss_culling": ("off" if args.no_cull else "on: a ray ends as a miss once its cell is beyond every grid row holding a solid voxel (occupancy summary) and "

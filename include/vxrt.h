@@ -45,7 +45,8 @@ typedef struct {
     int32_t grid_w, grid_h, grid_d;  /* voxel grid extents; reference: 512, 96, 512 (render.hpp:4-5) */
     int32_t width, height;           /* frame size in pixels (main.cpp:11-12, reshape render.cpp:404-411) */
     int32_t device;                  /* CUDA device ordinal */
-    int32_t rank, world;             /* image-tile partition: this context renders tiles t with t % world == rank */
+    int32_t rank, world;             /* image-tile partition: this context renders one tile of every group of `world` consecutive tiles
+                                        (rotated per tile row so that its tiles do not line up in columns; vxrt_set_partition) */
     uint32_t flags;
 } vxrt_config;
 
@@ -206,8 +207,8 @@ int vxrt_set_overlap(vxrt_ctx* ctx, int mode);
    blocks per SM) have the higher throughput.  Same pixels.  While fused, vxrt_get_stats cannot separate the passes
    (ms_primary = whole frame, ms_shadow = 0), and vxrt_set_overlap has no effect. */
 int vxrt_set_fusion(vxrt_ctx* ctx, int mode);
-/* Which image tiles a context of a multi-GPU split renders (all ranks must choose the same): 0 (default) tile t belongs to rank
-   t % world; 1 whole TILE ROWS are the interleaved unit -- tile row r belongs to rank r % world -- so that a rank's pixels are
+/* Which image tiles a context of a multi-GPU split renders (all ranks must choose the same): 0 (default) groups of `world`
+   consecutive tiles, one to each rank, rotated by the tile row the group starts in; 1 whole TILE ROWS are the interleaved unit -- tile row r belongs to rank r % world -- so that a rank's pixels are
    contiguous 8-row strips of the raster frame.  With 1, vxrt_render_to_host_frame renders into a local strip buffer and moves the
    strips into the shared host frame with ONE strided DMA on the copy stream (a DMA fills a PCIe link; stores from kernels reach
    about 40 % of it), overlapped with the next frame; local buffers / the all-gather layout become [local strip][8][width].

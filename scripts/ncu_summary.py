@@ -1,5 +1,5 @@
 """Summarise an `ncu --set full` report of the two render kernels into profiles/<name>.json (the file bench.py reads
-for roofline.traffic): python scripts/ncu_summary.py gpurun_out/prof_f.ncu-rep profiles/r1_ncu_traffic.json "<source note>"."""
+for roofline.traffic): python scripts/ncu_summary.py gpurun_out/prof_f.ncu-rep profiles/r2_ncu_traffic.json "<source note>" [workload]."""
 import csv
 import io
 import json
@@ -30,6 +30,7 @@ UNIT_SCALE = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "usecond": 
 
 def main():
     rep, out, note = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "")
+    workload = sys.argv[4] if len(sys.argv) > 4 else "C3ii_4k"
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -50,7 +51,7 @@ def main():
             x *= UNIT_SCALE.get(u.get(metric, ""), 1.0) if key.startswith(("dram", "duration")) else 1.0
             k[key] = round(x, 6)
         kernels[short] = k
-    json.dump({"workload": "C3ii_4k", "source": note, "kernels": kernels}, open(out, "w"), indent=1)
+    json.dump({"workload": workload, "source": note, "kernels": kernels}, open(out, "w"), indent=1)
     print(json.dumps(kernels, indent=1))
 
 

@@ -1,5 +1,5 @@
 """Every rank's share of an N-GPU split, one after the other on ONE GPU (no exchange): milliseconds per frame of each rank's kernels
-under the default switches, for both partitions (tile t -> rank t % N, tile row r -> rank r % N).  A frame of the split takes as long
+under the default switches, for both partitions (tiles dealt in groups of N with a per-row rotation, tile row r -> rank r % N).  A frame of the split takes as long
 as its slowest rank; the spread between the ranks is what no protocol work can remove.
 python scripts/rank_balance.py [--worlds 2 4 8] [--workload C3ii_4k]"""
 import argparse

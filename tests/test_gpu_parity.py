@@ -495,7 +495,7 @@ def test_update_partial_geometry_semantics(vx, oracle, default_level):
 @pytest.mark.parametrize("rows", [False, True], ids=["tiles", "tile_rows"])
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_tile_partition_reassembles_the_frame(vx, default_level, world, rows):
-    """both partitions (vxrt_set_partition): tile t -> rank t % world, and whole tile rows -> rank row % world (a rank's local
+    """both partitions (vxrt_set_partition): tiles dealt in groups of `world` (rotated per tile row), and whole tile rows -> rank row % world (a rank's local
     buffer is then its 8-row strips); 416x236: the last tile row is cut by the frame's edge"""
     import torch
     W, H = 416, 236

@@ -395,7 +395,7 @@ class Renderer:
         self._check(self.lib.vxrt_set_fusion(self._h, int(mode)))
 
     def setPartition(self, mode):
-        """0 tile t -> rank t % world (default), 1 tile row r -> rank r % world (a rank's pixels are 8-row strips: one strided DMA per frame)"""
+        """0 tiles dealt in groups of `world`, rotated per tile row (default), 1 tile row r -> rank r % world (a rank's pixels are 8-row strips: one strided DMA per frame)"""
         self._check(self.lib.vxrt_set_partition(self._h, int(mode)))
 
     def frameWasFused(self):

@@ -31,13 +31,25 @@ struct TileMap {
     int tx, ty, ntiles;                 // tiles per row / column / total
     int rank, world, nlocal;            // this context renders tiles t = j*world + rank, j in [0,nlocal)
     int tile_base;                      // first local tile of this launch (frames can be rendered in bands of tile rows)
+    const int2* tile_xy;                // optional, per local tile: pixel origin (x0, y0) of its global tile, y0 < 0 for padding tiles -- the host's
+                                        // statement of tile_of(), so that the render kernels need no integer division to find their pixels
     int rows;                           // 1: whole TILE ROWS are the interleaved unit (vxrt_set_partition): tile row r belongs to rank r % world,
                                         // local tile j = (local row j / tx, column j % tx); a rank's pixels are then contiguous 8-row strips
                                         // of the raster frame, which one strided DMA moves to a host frame
 };
+// Tile partition: the tiles are dealt in groups of `world` consecutive tiles (row-major), group j = tiles j*world .. j*world + world - 1,
+// one to each rank -- rotated by the tile row the group starts in, so that a rank's tiles do not line up in columns when the
+// number of tiles per row is a multiple of world (3840 / 32 = 120 tiles, 8 ranks: a rank would own every 8th 32-pixel column, and
+// vertical features of the scene -- tree trunks -- would land on one rank: measured 10 % above the mean for the slowest of 8).
+__host__ __device__ __forceinline__ int tile_rotation(const TileMap& m, int j) { return ((j * m.world) / m.tx) % m.world; }
 // global tile of local tile j (>= ntiles: padding)
 __host__ __device__ __forceinline__ int tile_of(const TileMap& m, int j) {
-    return m.rows ? ((j / m.tx) * m.world + m.rank) * m.tx + (j % m.tx) : j * m.world + m.rank;
+    return m.rows ? ((j / m.tx) * m.world + m.rank) * m.tx + (j % m.tx) : j * m.world + (m.rank + tile_rotation(m, j)) % m.world;
+}
+// rank that owns global tile t (tile partition)
+__host__ __device__ __forceinline__ int tile_owner(const TileMap& m, int t) {
+    const int j = t / m.world;
+    return (t % m.world - tile_rotation(m, j) + m.world) % m.world;
 }
 
 struct Counters {
@@ -95,10 +107,18 @@ __device__ __forceinline__ uint32_t out_index_of(const TileMap& m, int raster, i
 template <bool COUNT, class Grid, bool TRAV>
 __device__ __forceinline__ bool primary_pixel(const Grid& g, const FrameParams& f, const TileMap& m, const Outputs& o, int local_tile,
                                               int warp, int lane, RayHit& r, uint32_t& pid) {
-    const int t = tile_of(m, local_tile);                           // global tile
     const int lx = (warp & 3) * 8 + (lane & 7), ly = (warp >> 2) * 4 + (lane >> 3);
-    const int px = (t % m.tx) * TILE_W + lx, py = (t / m.tx) * TILE_H + ly;
-    const bool valid = (t < m.ntiles) && (px < m.width) && (py < m.height);
+    int x0, y0;
+    bool tile_ok;
+    if (m.tile_xy) {                                                 // the partition, tabulated by the host (vxrt.cu alloc_frame_buffers)
+        const int2 o2 = __ldg(m.tile_xy + local_tile);
+        x0 = o2.x; y0 = o2.y; tile_ok = y0 >= 0;
+    } else {
+        const int t = tile_of(m, local_tile);                        // global tile
+        x0 = (t % m.tx) * TILE_W; y0 = (t / m.tx) * TILE_H; tile_ok = t < m.ntiles;
+    }
+    const int px = x0 + lx, py = y0 + ly;
+    const bool valid = tile_ok && (px < m.width) && (py < m.height);
     bool hit = false;
     r.steps = 0; r.idx = -1;
     pid = (uint32_t)(py * m.width + px);
@@ -685,7 +705,7 @@ __global__ void assemble_kernel(const uint32_t* __restrict__ gathered, uint32_t*
         return;
     }
     const int t = (py / TILE_H) * m.tx + (px / TILE_W);
-    const int rank = t % m.world, local = t / m.world;
+    const int rank = tile_owner(m, t), local = t / m.world;
     dst[p] = gathered[((size_t)rank * m.nlocal + local) * TILE_PIX + (py % TILE_H) * TILE_W + (px % TILE_W)];
 }
 

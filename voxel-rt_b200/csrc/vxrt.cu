@@ -82,6 +82,12 @@ struct vxrt_ctx {
     uint32_t* d_shade_cost = nullptr;   // per shade unit: block cycles of the last shade pass
     uint32_t* d_shade_order = nullptr;
     bool have_tile_order = false, have_shade_order = false;
+    uint32_t* d_tile_order_back = nullptr;     // the sorts write here (side stream); adopted by a later frame (adopt_launch_orders)
+    uint32_t* d_shade_order_back = nullptr;
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_order_src = nullptr, ev_order_done = nullptr;
+    bool order_pending = false, pend_tiles = false, pend_shade = false;
+    int pend_shade_threads = 0;
     int order_shade_threads = 0;        // block size the shade order was recorded with
     unsigned long long order_frame = 0; // whole-frame launches since the ordering was (re)started
     bool use_tile_order = true;
@@ -90,6 +96,7 @@ struct vxrt_ctx {
     int overlap = 0;                    // vxrt_set_overlap: 0 off (default), 1 on, 2 auto (on when this context renders <= 12,000 tiles) -- the shade
                                         // pass starts inside the primary pass's tail (programmatic dependent launch + per-tile flags)
     uint32_t* d_tile_ready = nullptr;   // per local tile: frame_seq of the last primary pass that finished it
+    int2* d_tile_xy = nullptr;          // per local tile: pixel origin of its global tile (TileMap::tile_xy)
     int* d_overlap_err = nullptr;
     uint32_t frame_seq = 0;
     bool last_fused = false;            // the last frame ran as one fused kernel
@@ -136,6 +143,7 @@ static TileMap make_map(int width, int height, int rank, int world, bool rows) {
     m.rows = (rows && world > 1) ? 1 : 0;
     m.nlocal = m.rows ? ((m.ty + world - 1) / world) * m.tx : (m.ntiles + world - 1) / world;
     m.tile_base = 0;
+    m.tile_xy = nullptr;
     return m;
 }
 
@@ -155,10 +163,14 @@ static GridView grid_view(const vxrt_ctx* c) {
     return g;
 }
 
+static void drop_pending_orders(vxrt_ctx* c);
 static void free_frame_buffers(vxrt_ctx* c) {
+    drop_pending_orders(c);
+    cudaFree(c->d_tile_order_back); cudaFree(c->d_shade_order_back); c->d_tile_order_back = nullptr; c->d_shade_order_back = nullptr;
     cudaFree(c->d_rgba8); cudaFree(c->d_rgba8_alt); cudaFree(c->d_hitq); cudaFree(c->d_hitpix);
     cudaFree(c->d_tile_cost); cudaFree(c->d_tile_order); cudaFree(c->d_tile_hits); cudaFree(c->d_shade_cost); cudaFree(c->d_shade_order);
     cudaFree(c->d_tile_ready); c->d_tile_ready = nullptr;
+    cudaFree(c->d_tile_xy); c->d_tile_xy = nullptr; c->map.tile_xy = nullptr;
     c->d_last_frame = nullptr;
     c->d_tile_cost = nullptr; c->d_tile_order = nullptr; c->d_tile_hits = nullptr; c->d_shade_cost = nullptr; c->d_shade_order = nullptr;
     c->have_tile_order = false; c->have_shade_order = false; c->order_frame = 0;
@@ -175,6 +187,17 @@ static int alloc_frame_buffers(vxrt_ctx* c) {
     c->map = make_map(c->cfg.width, c->cfg.height, c->cfg.rank, c->cfg.world, c->row_partition);
     const size_t npix = (size_t)c->cfg.width * c->cfg.height;
     const size_t local_pix = (size_t)c->map.nlocal * TILE_PIX;
+    {   // the partition as a table: pixel origin of every local tile's global tile (y < 0: padding)
+        std::vector<int2> xy((size_t)c->map.nlocal);
+        for (int j = 0; j < c->map.nlocal; j++) {
+            const int t = tile_of(c->map, j);
+            xy[(size_t)j] = (t < c->map.ntiles) ? make_int2((t % c->map.tx) * TILE_W, (t / c->map.tx) * TILE_H) : make_int2(0, -1);
+        }
+        CUDA_TRY(cudaMalloc(&c->d_tile_xy, xy.size() * sizeof(int2)));
+        CUDA_TRY(cudaMemcpyAsync(c->d_tile_xy, xy.data(), xy.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->map.tile_xy = c->d_tile_xy;
+    }
     c->out_pixels = (c->cfg.world == 1) ? npix : local_pix;
     CUDA_TRY(cudaMalloc(&c->d_rgba8, c->out_pixels * 4));
     CUDA_TRY(cudaMemsetAsync(c->d_rgba8, 0, c->out_pixels * 4, c->stream));
@@ -182,6 +205,8 @@ static int alloc_frame_buffers(vxrt_ctx* c) {
     CUDA_TRY(cudaMalloc(&c->d_hitpix, local_pix * 4));
     CUDA_TRY(cudaMalloc(&c->d_tile_cost, (size_t)c->map.nlocal * 4));
     CUDA_TRY(cudaMalloc(&c->d_tile_order, (size_t)c->map.nlocal * 4));
+    CUDA_TRY(cudaMalloc(&c->d_tile_order_back, (size_t)c->map.nlocal * 4));
+    CUDA_TRY(cudaMalloc(&c->d_shade_order_back, (size_t)c->map.nlocal * 4 * 4));
     CUDA_TRY(cudaMalloc(&c->d_tile_hits, (size_t)c->map.nlocal * 4));
     CUDA_TRY(cudaMalloc(&c->d_tile_ready, (size_t)c->map.nlocal * 4));
     CUDA_TRY(cudaMemsetAsync(c->d_tile_ready, 0, (size_t)c->map.nlocal * 4, c->stream));
@@ -385,6 +410,9 @@ extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     for (auto& e : c->ev_band_start) if (cudaEventCreate(&e) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
     if (cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
     for (auto& e : c->ev_slot) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
+    if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaStreamCreate failed"));
+    if (cudaEventCreateWithFlags(&c->ev_order_src, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_order_done, cudaEventDisableTiming) != cudaSuccess)
+        return bail(fail(VXRT_ERR_CUDA, "cudaEventCreate failed"));
     if (cudaMalloc(&c->d_counters, sizeof(Counters) * MAX_BANDS) != cudaSuccess) return bail(fail(VXRT_ERR_CUDA, "cudaMalloc(counters) failed"));
     int rc = upload_depth_offsets();
     if (rc != VXRT_OK) return bail(rc);
@@ -428,6 +456,9 @@ extern "C" void vxrt_destroy(vxrt_ctx* c) {
     for (auto& e : c->ev_band_start) if (e) cudaEventDestroy(e);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     for (auto& e : c->ev_slot) if (e) cudaEventDestroy(e);
+    if (c->ev_order_src) cudaEventDestroy(c->ev_order_src);
+    if (c->ev_order_done) cudaEventDestroy(c->ev_order_done);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -879,6 +910,44 @@ extern "C" int vxrt_resize(vxrt_ctx* c, int width, int height) {                
 // Launches the frame's kernels in `nbands` bands of whole tile rows.  host_dst != nullptr: each band's pixels are
 // copied to host_dst (page-locked) on the copy stream as soon as the band's kernels finish, so the read-back of
 // band b overlaps the rendering of band b+1.
+// ---- launch orders (slowest block first), refreshed OFF the frame's stream --------------------------------------------------
+// The one-block counting sorts take 37 us (32,400 tiles) + 70 us (64,800 shade units) for a whole 4K frame.  The order they
+// produce is a hint for LATER frames, so they run on a side stream, behind the frame that produced the block times, into the
+// back buffers; a later render call adopts the result once the sort's event has completed (pointer swap, no synchronisation).
+static void adopt_launch_orders(vxrt_ctx* c) {
+    if (!c->order_pending) return;
+    const cudaError_t e = cudaEventQuery(c->ev_order_done);
+    if (e == cudaErrorNotReady) { cudaGetLastError(); return; }
+    c->order_pending = false;
+    if (e != cudaSuccess) { cudaGetLastError(); return; }
+    if (c->pend_tiles) { std::swap(c->d_tile_order, c->d_tile_order_back); c->have_tile_order = true; }
+    if (c->pend_shade) { std::swap(c->d_shade_order, c->d_shade_order_back); c->have_shade_order = true; c->order_shade_threads = c->pend_shade_threads; }
+}
+// forget a sort in flight (the block times it reads are about to mean something else, or its buffers are about to go)
+static void drop_pending_orders(vxrt_ctx* c) {
+    if (c->aux_stream) { cudaStreamSynchronize(c->aux_stream); cudaGetLastError(); }
+    c->order_pending = false;
+}
+static int refresh_launch_orders(vxrt_ctx* c, bool tiles, bool shade) {
+    if (c->order_pending) return VXRT_OK;                 // the previous refresh has not been adopted yet
+    CUDA_TRY(cudaEventRecord(c->ev_order_src, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_order_src, 0));
+    if (tiles) {
+        tile_order_kernel<<<1, 1024, 0, c->aux_stream>>>(c->d_tile_cost, c->d_tile_order_back, c->map.nlocal);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+    }
+    if (shade) {
+        const int upt = TILE_PIX / c->shade_threads;
+        tile_order_kernel<<<1, 1024, 0, c->aux_stream>>>(c->d_shade_cost, c->d_shade_order_back, c->map.nlocal * upt);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_order_done, c->aux_stream));
+    c->order_pending = true; c->pend_tiles = tiles; c->pend_shade = shade; c->pend_shade_threads = c->shade_threads;
+    return VXRT_OK;
+}
+
 static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* dev_out = nullptr, bool fence_main = true, bool raster_out = false,
                         bool local_out = false) {
     const bool p2p_frame = c->p2p && !raster_out && !local_out;   // a host-frame render of a peer-memory context leaves the peer frame alone
@@ -887,6 +956,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         for (int slot = 0; slot < 2; slot++)
             if (c->slot_busy[slot]) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_slot[slot], 0));
     if (!c->grid_loaded) return fail(VXRT_ERR_STATE, "render before any grid upload");
+    adopt_launch_orders(c);
     const GridView g = grid_view(c);
     FrameParams fp;
     memcpy(&fp, &c->frame, sizeof fp);
@@ -1028,15 +1098,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
             c->launches++;
             pdl_first = false;
             if (!pdl_chain) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));   // (one kernel: ms_primary reads as the whole frame, ms_shadow as 0)
-            if (o.tile_cost && c->map.nlocal >= 64 && (c->order_frame < 2 || (c->order_frame % 8) == 0)) {
-                if (pdl_chain) refresh_tiles_later = true;
-                else {
-                    tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_tile_cost, c->d_tile_order, c->map.nlocal);
-                    CUDA_TRY(cudaGetLastError());
-                    c->launches++;
-                    c->have_tile_order = true;
-                }
-            }
+            refresh_tiles_later = o.tile_cost && c->map.nlocal >= 64 && (c->order_frame < 2 || (c->order_frame % 8) == 0);
         } else {
         o.pdl_wait = pdl_first ? 1 : 0; o.pdl_trigger = (pdl_chain && !shade_follows) ? 1 : 0;
         VXRT_LAUNCH(primary_kernel, count_primary, trav_primary, grid, block, pdl_first);
@@ -1045,20 +1107,10 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         pdl_first = false;
         o.pdl_wait = 0; o.pdl_trigger = (pdl_chain && shade_follows) ? 1 : 0;
         if (nbands == 1 && !overlap && !(pdl_chain && !shade_follows)) { CUDA_TRY(cudaEventRecord(c->ev[1], c->stream)); ev1_recorded = true; }
-        // the launch orders are refreshed on the first two frames and then every 8th (block times are temporally
-        // coherent; the one-block sort costs ~30 us at 4K)
+        // the launch orders are refreshed on the first two frames and then every 8th (block times are temporally coherent), behind
+        // the frame and off its stream (refresh_launch_orders below)
         const bool refresh_order = c->order_frame < 2 || (c->order_frame % 8) == 0;
-        auto refresh_tile_order = [&]() -> int {
-            if (pdl_chain) { refresh_tiles_later = o.tile_cost && c->map.nlocal >= 64 && refresh_order; return VXRT_OK; }
-            if (o.tile_cost && c->map.nlocal >= 64 && refresh_order) {
-                tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_tile_cost, c->d_tile_order, c->map.nlocal);
-                CUDA_TRY(cudaGetLastError());
-                c->launches++;
-                c->have_tile_order = true;
-            }
-            return VXRT_OK;
-        };
-        if (!overlap) { const int rc = refresh_tile_order(); if (rc != VXRT_OK) return rc; }
+        refresh_tiles_later = o.tile_cost && c->map.nlocal >= 64 && refresh_order;
         if (c->frame.view_depth_field != 1) {
             const dim3 sblock(c->shade_threads), sgrid((unsigned)(((size_t)ntile * TILE_PIX + c->shade_threads - 1) / c->shade_threads));
             VXRT_LAUNCH(shade_kernel, count, trav_shade, sgrid, sblock, overlap);
@@ -1067,16 +1119,8 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
             if (overlap) {
                 CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));      // (the passes overlap: ms_primary then reads as the whole frame, ms_shadow as 0)
                 ev1_recorded = true;
-                const int rc = refresh_tile_order(); if (rc != VXRT_OK) return rc;
             }
-            if (pdl_chain) refresh_shade_later = o.shade_cost && c->map.nlocal >= 64 && refresh_order;
-            else if (o.shade_cost && c->map.nlocal >= 64 && refresh_order) {
-                tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_shade_cost, c->d_shade_order, c->map.nlocal * upt);
-                CUDA_TRY(cudaGetLastError());
-                c->launches++;
-                c->have_shade_order = true;
-                c->order_shade_threads = c->shade_threads;
-            }
+            refresh_shade_later = o.shade_cost && c->map.nlocal >= 64 && refresh_order;
         }
         }   // two passes
         if (host_dst) {
@@ -1107,20 +1151,6 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         c->p2p_seq++;
         if (!ev1_recorded) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));   // (one render kernel: ms_primary reads as the whole frame)
         CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
-        if (refresh_tiles_later) {
-            tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_tile_cost, c->d_tile_order, c->map.nlocal);
-            CUDA_TRY(cudaGetLastError());
-            c->launches++;
-            c->have_tile_order = true;
-        }
-        if (refresh_shade_later) {
-            const int upt = TILE_PIX / c->shade_threads;
-            tile_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_shade_cost, c->d_shade_order, c->map.nlocal * upt);
-            CUDA_TRY(cudaGetLastError());
-            c->launches++;
-            c->have_shade_order = true;
-            c->order_shade_threads = c->shade_threads;
-        }
         if (nbands == 1 && c->use_tile_order) c->order_frame++;
     } else {
     if (nbands != 1) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -1132,6 +1162,10 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         c->launches++;
         c->p2p_seq++;
     }
+    }
+    if (refresh_tiles_later || refresh_shade_later) {
+        const int rc = refresh_launch_orders(c, refresh_tiles_later, refresh_shade_later);
+        if (rc != VXRT_OK) return rc;
     }
     if (host_dst && fence_main) {                         // later work on the main stream must not overwrite pixels in flight
         CUDA_TRY(cudaEventRecord(c->ev_copy, c->copy_stream));
@@ -1189,7 +1223,7 @@ extern "C" int vxrt_download_traversal(vxrt_ctx* c, int32_t* out, size_t count) 
 extern "C" int vxrt_set_fusion(vxrt_ctx* c, int mode) {
     if (!c) return fail(VXRT_ERR_INVALID, "null context");
     if (mode < 0 || mode > 2) return fail(VXRT_ERR_INVALID, "set_fusion: 0 two passes, 1 fused, 2 auto");
-    if (mode != c->fusion) { c->have_tile_order = false; c->have_shade_order = false; c->order_frame = 0; }   // block times mean something else now
+    if (mode != c->fusion) { drop_pending_orders(c); c->have_tile_order = false; c->have_shade_order = false; c->order_frame = 0; }   // block times mean something else now
     c->fusion = mode;
     return VXRT_OK;
 }
@@ -1216,6 +1250,7 @@ extern "C" int vxrt_set_overlap(vxrt_ctx* c, int mode) {
 extern "C" int vxrt_set_tile_ordering(vxrt_ctx* c, int enabled) {
     if (!c) return fail(VXRT_ERR_INVALID, "null context");
     c->use_tile_order = enabled != 0;
+    drop_pending_orders(c);
     if (!enabled) { c->have_tile_order = false; c->have_shade_order = false; }
     c->order_frame = 0;
     return VXRT_OK;

@@ -1,5 +1,5 @@
-"""Sort-first image-tile partition: the frame is cut into 32x8-pixel tiles, tile t belongs to
-rank t % world, each rank renders its tiles into a compact [nlocal][8][32] RGBA8 buffer (the gather layout),
+"""Sort-first image-tile partition: the frame is cut into 32x8-pixel tiles, dealt in groups of `world`
+consecutive tiles, one to each rank (rotated per tile row, see tile_owner), each rank renders its tiles into a compact [nlocal][8][32] RGBA8 buffer (the gather layout),
 one all-gather collects them and `assemble` un-tiles into the raster frame.  This module is the host-side
 (numpy) statement of that mapping; libvxrt's TileMap / assemble_kernel implement the same arithmetic.
 
@@ -24,11 +24,20 @@ def local_tiles(width, height, world, rows=False):
     return (n + world - 1) // world
 
 
+def tile_owner(t, tx, world):
+    """rank of global tile t: groups of `world` consecutive tiles are dealt one to each rank, rotated by the tile row the group
+    starts in (a rank's tiles then do not line up in columns when tx is a multiple of world)"""
+    t = np.asarray(t)
+    j = t // world
+    return (t % world - ((j * world) // tx) % world) % world
+
+
 def tiles_of_rank(width, height, rank, world, rows=False):
     tx, ty, ntiles = tile_counts(width, height)
     if rows and world > 1:
         return np.concatenate([np.arange(r * tx, (r + 1) * tx) for r in range(rank, ty, world)] or [np.zeros(0, np.int64)])
-    return np.arange(rank, ntiles, world)
+    t = np.arange(ntiles)
+    return t[tile_owner(t, tx, world) == rank]
 
 
 def pixel_owner(width, height, world, rows=False):
@@ -37,7 +46,7 @@ def pixel_owner(width, height, world, rows=False):
     py, px = np.mgrid[0:height, 0:width]
     if rows and world > 1:
         return (py // TILE_H) % world
-    return ((py // TILE_H) * tx + px // TILE_W) % world
+    return tile_owner((py // TILE_H) * tx + px // TILE_W, tx, world)
 
 
 def extract_local(frame, rank, world, rows=False):
@@ -70,4 +79,4 @@ def assemble(gathered, width, height, rows=False):
         row = py // TILE_H
         return g[row % world, ((row // world) * TILE_H + py % TILE_H) * width + px]
     t = (py // TILE_H) * tx + px // TILE_W
-    return gathered[t % world, t // world, py % TILE_H, px % TILE_W]
+    return gathered[tile_owner(t, tx, world), t // world, py % TILE_H, px % TILE_W]
