@@ -214,6 +214,36 @@ def test_pipelined_frame_submission(vx, oracle, default_level):
         assert np.array_equal(r.renderFrameHost(to_vx_frame(vx, gc.frame_cases(W, H)["C1"])), bufs[4])
 
 
+def test_back_to_back_frames_across_launch_order_refreshes(vx, oracle, default_level):
+    """100 frames queued back to back (no synchronisation in between), alternating two poses so that a tile a bad launch order
+    drops would keep the OTHER pose's pixels: the launch orders are refreshed from the block times on a side stream while the
+    next frames already overwrite those times (the sorts work on a snapshot), and adopted by a later frame; every sampled
+    frame must equal the oracle, and the counted rays of a frame rendered with adopted orders must equal a fresh context's"""
+    W, H = 416, 240
+    cases = gc.frame_cases(W, H)
+    names = ["C2", "C3ii_pitched"]
+    want = [oracle.render(default_level, gc.DIMS, cases[n], W, H)["rgba8"] for n in names]
+    for fusion in (0, 1):
+        with vx.Renderer(grid=gc.DIMS, width=W, height=H) as r:
+            r.updateGeometry(default_level)
+            r.setFusion(fusion)
+            bufs = [r.hostFrameBuffer() for _ in range(4)]
+            for k in range(100):
+                r.submitFrameHost(to_vx_frame(vx, cases[names[k & 1]]), bufs[k & 3])
+            r.waitFrames()
+            for j in range(4):                                       # frames 96..99
+                assert np.array_equal(bufs[j], want[j & 1]), (fusion, j)
+            r.setStats(True)
+            r.updateUniforms(to_vx_frame(vx, cases["C2"])); r.draw(); st = r.stats()
+            assert np.array_equal(r.readPixels(), want[0])
+        with vx.Renderer(grid=gc.DIMS, width=W, height=H) as fresh:
+            fresh.updateGeometry(default_level)
+            fresh.setStats(True)
+            fresh.updateUniforms(to_vx_frame(vx, cases["C2"])); fresh.draw(); st0 = fresh.stats()
+        for key in ("rays_primary", "rays_global", "rays_local", "fetches", "hit_pixels"):
+            assert st[key] == st0[key], (fusion, key, st[key], st0[key])
+
+
 def test_miss_culling_never_changes_a_frame(vx, oracle, default_level):
     """production kernels end a ray as a miss once its cell is beyond every row that holds a solid voxel (ray.cuh CULL);
     frames must equal the counted (uncullled) variants and the oracle for cameras above / inside / below the solid rows,

@@ -84,6 +84,7 @@ struct vxrt_ctx {
     bool have_tile_order = false, have_shade_order = false;
     uint32_t* d_tile_order_back = nullptr;     // the sorts write here (side stream); adopted by a later frame (adopt_launch_orders)
     uint32_t* d_shade_order_back = nullptr;
+    uint32_t* d_cost_snap = nullptr;           // snapshot of the block times the sorts read: [nlocal] tiles, then [nlocal * 4] shade units
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_order_src = nullptr, ev_order_done = nullptr;
     bool order_pending = false, pend_tiles = false, pend_shade = false;
@@ -167,6 +168,7 @@ static void drop_pending_orders(vxrt_ctx* c);
 static void free_frame_buffers(vxrt_ctx* c) {
     drop_pending_orders(c);
     cudaFree(c->d_tile_order_back); cudaFree(c->d_shade_order_back); c->d_tile_order_back = nullptr; c->d_shade_order_back = nullptr;
+    cudaFree(c->d_cost_snap); c->d_cost_snap = nullptr;
     cudaFree(c->d_rgba8); cudaFree(c->d_rgba8_alt); cudaFree(c->d_hitq); cudaFree(c->d_hitpix);
     cudaFree(c->d_tile_cost); cudaFree(c->d_tile_order); cudaFree(c->d_tile_hits); cudaFree(c->d_shade_cost); cudaFree(c->d_shade_order);
     cudaFree(c->d_tile_ready); c->d_tile_ready = nullptr;
@@ -207,6 +209,7 @@ static int alloc_frame_buffers(vxrt_ctx* c) {
     CUDA_TRY(cudaMalloc(&c->d_tile_order, (size_t)c->map.nlocal * 4));
     CUDA_TRY(cudaMalloc(&c->d_tile_order_back, (size_t)c->map.nlocal * 4));
     CUDA_TRY(cudaMalloc(&c->d_shade_order_back, (size_t)c->map.nlocal * 4 * 4));
+    CUDA_TRY(cudaMalloc(&c->d_cost_snap, (size_t)c->map.nlocal * 5 * 4));
     CUDA_TRY(cudaMalloc(&c->d_tile_hits, (size_t)c->map.nlocal * 4));
     CUDA_TRY(cudaMalloc(&c->d_tile_ready, (size_t)c->map.nlocal * 4));
     CUDA_TRY(cudaMemsetAsync(c->d_tile_ready, 0, (size_t)c->map.nlocal * 4, c->stream));
@@ -930,16 +933,21 @@ static void drop_pending_orders(vxrt_ctx* c) {
 }
 static int refresh_launch_orders(vxrt_ctx* c, bool tiles, bool shade) {
     if (c->order_pending) return VXRT_OK;                 // the previous refresh has not been adopted yet
+    // The sort reads every block time twice (histogram pass, scatter pass) while the NEXT frame's kernels already overwrite them:
+    // it must work on a snapshot, or the two passes disagree and the "order" is no permutation (tiles rendered twice / never).
+    // The snapshots are small device-to-device copies on the frame's own stream (130 KB + 260 KB for a whole 4K frame).
+    const int upt = TILE_PIX / c->shade_threads;
+    if (tiles) CUDA_TRY(cudaMemcpyAsync(c->d_cost_snap, c->d_tile_cost, (size_t)c->map.nlocal * 4, cudaMemcpyDeviceToDevice, c->stream));
+    if (shade) CUDA_TRY(cudaMemcpyAsync(c->d_cost_snap + c->map.nlocal, c->d_shade_cost, (size_t)c->map.nlocal * upt * 4, cudaMemcpyDeviceToDevice, c->stream));
     CUDA_TRY(cudaEventRecord(c->ev_order_src, c->stream));
     CUDA_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_order_src, 0));
     if (tiles) {
-        tile_order_kernel<<<1, 1024, 0, c->aux_stream>>>(c->d_tile_cost, c->d_tile_order_back, c->map.nlocal);
+        tile_order_kernel<<<1, 1024, 0, c->aux_stream>>>(c->d_cost_snap, c->d_tile_order_back, c->map.nlocal);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
     }
     if (shade) {
-        const int upt = TILE_PIX / c->shade_threads;
-        tile_order_kernel<<<1, 1024, 0, c->aux_stream>>>(c->d_shade_cost, c->d_shade_order_back, c->map.nlocal * upt);
+        tile_order_kernel<<<1, 1024, 0, c->aux_stream>>>(c->d_cost_snap + c->map.nlocal, c->d_shade_order_back, c->map.nlocal * upt);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
     }
