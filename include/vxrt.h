@@ -214,6 +214,12 @@ int vxrt_set_fusion(vxrt_ctx* ctx, int mode);
    about 40 % of it), overlapped with the next frame; local buffers / the all-gather layout become [local strip][8][width].
    Re-allocates the per-frame buffers.  Same pixels. */
 int vxrt_set_partition(vxrt_ctx* ctx, int mode);
+/* Fused frames only: how many of the heaviest tiles (previous frames' block times) are rendered by TWO blocks each with two threads
+   per hit pixel -- one evaluates the global shadow ray and the first half of the active lights, the other the second half without
+   the early-out; the terms are combined in slot order afterwards (what a light adds does not depend on the multiplier,
+   fshader.glsl:161-179), so the pixel is the same.  A small share of a frame lasts as long as its slowest block; this halves that
+   block's sequential chain.  0 = off, default 8, at most 64.  Same pixels. */
+int vxrt_set_wide_tiles(vxrt_ctx* ctx, int tiles);
 /* 1 when the last vxrt_render ran as one fused kernel (see vxrt_set_fusion), else 0. */
 int vxrt_frame_was_fused(vxrt_ctx* ctx);
 /* mode 0 (default) = the production kernels: no per-iteration counter, rays that cannot change a pixel are not traced
@@ -257,6 +263,9 @@ int vxrt_cast_rays(vxrt_ctx* ctx, int32_t n, const float* starts, const float* d
 /* device self-test of the kernels' exact division-by-ray-direction (ray.cuh div_by) against IEEE division on n
    pseudo-random operand pairs inside its documented domain; *mismatches must come back 0 */
 int vxrt_selftest_division(vxrt_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches);
+/* device self-test of the kernels' step reciprocals 1 / |dir + 0.000001| (fshader.glsl:74-76; ray.cuh refined_rcp) against the
+   IEEE reciprocal on EVERY float of [2^-40, 4); *mismatches must come back 0 */
+int vxrt_selftest_reciprocal(vxrt_ctx* ctx, uint64_t* mismatches);
 /* binary PPM (P6), rows flipped so the image is upright */
 int vxrt_write_ppm(vxrt_ctx* ctx, const char* path);
 

@@ -89,6 +89,11 @@ def test_tie_lock_ray(vx, oracle, default_level, ren):
         assert np.array_equal(out7[k][:3].view(np.uint32), hp.view(np.uint32)) and list(out7[k][3:6]) == list(hn) and out7[k][6] == st
 
 
+def test_step_reciprocals_match_ieee(vx, ren):
+    """ray.cuh: 1 / |dir + 0.000001| through refined_rcp == rcp.rn on every float of [2^-40, 4)"""
+    assert ren.selftestReciprocal() == 0
+
+
 def test_fast_division_matches_ieee(vx, ren):
     """ray.cuh div_by (hoisted reciprocal + 3 FFMA) == __fdiv_rn on 2^31 random operand pairs of its domain"""
     assert ren.selftestDivision(1 << 31, seed=12345) == 0
@@ -1048,6 +1053,54 @@ def test_fused_and_overlapped_frames_render_the_same_pixels(vx, oracle, default_
                 r.draw()
             parts.append(r.readPixels())
     assert np.array_equal(vx.tiles.assemble(np.stack(parts), W, H), want)
+
+
+def test_wide_tiles_render_the_same_pixels(vx, oracle, default_level):
+    """vxrt_set_wide_tiles: the heaviest tiles of a fused frame get two blocks and two threads per hit pixel -- one walks the
+    global shadow ray and the first half of the active lights, the other the second half without the early-out, combined in slot
+    order afterwards.  Same pixels as the oracle with 0 / 8 / 64 wide tiles: light sets whose overbright clamp ends the loop in
+    the first half, in the second half or never; gaps between the slots; negative / infinite / NaN weights; an odd number of
+    lights; culling off (unlit rays traced)"""
+    import oracle_lib as ol
+    W, H = 640, 360
+    aspect = np.float32(W) / np.float32(H)
+    cam = gc.CAM
+    near = [(cam[0] + dx, 40.0 + (k % 3), cam[2] + 20.0 + dz, w) for k, (dx, dz, w) in enumerate(
+        [(-12, 0, 0.5), (-8, 6, 0.5), (-4, 12, 0.5), (0, 18, 0.5), (4, 24, 0.5), (8, 30, 0.5), (12, 36, 0.5), (-10, 40, 0.5),
+         (-6, 34, 0.5), (-2, 28, 0.5), (2, 22, 0.5), (6, 16, 0.5), (10, 10, 0.5), (14, 4, 0.5), (-14, 8, 0.5), (0, 44, 0.5)])]
+    gaps = [(-1, -1, -1, 0)] * 16
+    for slot, l in zip((1, 2, 6, 7, 8, 13, 15), near):
+        gaps[slot] = l
+    frames = {
+        "strong_16": ol.make_frame(cam, aspect=aspect, lights=near),                                    # clamp early (first half)
+        "weak_16": ol.make_frame(cam, aspect=aspect, lights=[(x, y, z, 0.07) for x, y, z, _ in near]),   # clamp late or never
+        "mixed_16": ol.make_frame(cam, aspect=aspect, lights=[(x, y, z, 0.02 if k < 8 else 0.6) for k, (x, y, z, _) in enumerate(near)]),
+        "gaps_7": ol.make_frame(cam, aspect=aspect, lights=gaps),
+        "odd_5": ol.make_frame(cam, aspect=aspect, lights=near[:5]),
+        "weird": ol.make_frame(cam, aspect=aspect, lights=[(190.0, 40.0, 170.0, -0.5), (200.0, 45.0, 180.0, float("inf")), (185.0, 39.0, 165.0, float("nan")),
+                                                            (205.0, 38.0, 160.0, 1e38), (195.0, 60.0, 175.0, 0.0), (192.0, 41.0, 172.0, 0.3)]),
+        "pitched": gc.frame_cases(W, H)["C3ii_pitched"],
+        "one_light": ol.make_frame(cam, aspect=aspect, lights=near[:1]),
+        "no_lights": gc.frame_cases(W, H)["C1"],
+    }
+    want = {n: oracle.render(default_level, gc.DIMS, fr, W, H)["rgba8"] for n, fr in frames.items()}
+    with vx.Renderer(grid=gc.DIMS, width=W, height=H) as r:
+        r.updateGeometry(default_level)
+        r.setFusion(1)
+        r.setStats(False)
+        for culling in (True, False):
+            r.setCulling(culling)
+            for wide in (64, 8, 0):
+                r.setWideTiles(wide)
+                for rep in range(2):
+                    for n, fr in frames.items():
+                        r.updateUniforms(to_vx_frame(vx, fr))
+                        r.draw(); r.draw(); r.draw()                   # (the launch order -- which tiles are wide -- settles over frames)
+                        got = r.readPixels()
+                        bad = int((got != want[n]).any(axis=2).sum())
+                        assert bad == 0, (culling, wide, rep, n, bad)
+        with pytest.raises(vx.VxrtError):
+            r.setWideTiles(65)
 
 
 def test_remove_sphere_from_a_device_side_command(vx, oracle, default_level):

@@ -88,6 +88,7 @@ _SIGNATURES = {
     "vxrt_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_fusion": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_frame_was_fused": (C.c_int, [C.c_void_p]),
+    "vxrt_set_wide_tiles": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_partition": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_render_frame_host": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p]),
@@ -99,6 +100,7 @@ _SIGNATURES = {
     "vxrt_read_block_costs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "vxrt_cast_rays": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vxrt_selftest_division": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "vxrt_selftest_reciprocal": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "vxrt_write_ppm": (C.c_int, [C.c_void_p, C.c_char_p]),
     "vxrt_local_tiles": (C.c_size_t, [C.c_void_p]),
     "vxrt_local_bytes": (C.c_size_t, [C.c_void_p]),
@@ -398,6 +400,10 @@ class Renderer:
         """0 tiles dealt in groups of `world`, rotated per tile row (default), 1 tile row r -> rank r % world (a rank's pixels are 8-row strips: one strided DMA per frame)"""
         self._check(self.lib.vxrt_set_partition(self._h, int(mode)))
 
+    def setWideTiles(self, tiles):
+        """fused frames: the `tiles` heaviest tiles get two blocks / two threads per hit pixel (0 off, default 8)"""
+        self._check(self.lib.vxrt_set_wide_tiles(self._h, int(tiles)))
+
     def frameWasFused(self):
         """the last draw() ran as one fused kernel (setFusion)"""
         return bool(self.lib.vxrt_frame_was_fused(self._h))
@@ -492,6 +498,11 @@ class Renderer:
     def selftestDivision(self, n, seed=1):
         bad = C.c_uint64(0)
         self._check(self.lib.vxrt_selftest_division(self._h, int(n), int(seed), C.byref(bad)))
+        return int(bad.value)
+
+    def selftestReciprocal(self):
+        bad = C.c_uint64(0)
+        self._check(self.lib.vxrt_selftest_reciprocal(self._h, C.byref(bad)))
         return int(bad.value)
 
     def writePPM(self, path):

@@ -102,6 +102,10 @@ VARIANTS = {
     # bench.py's "experiments" object times every entry).  Round 1's late_domain_check is the default now, jump_prefetch
     # (a measured loss) is gone.
     "early_domain_check": ["-DVXRT_EARLY_DOMAIN_CHECK"],    # test the fast domain of a jump's re-base before dividing (ray.cuh; round 1's order)
+    "early_check_primary": ["-DVXRT_EARLY_DOMAIN_CHECK_PRIMARY"],   # ... in the compiler-scheduled loop (primary rays) only
+    # measured and dropped (round 2, call 15; the macros remain): -DVXRT_EXP_STREAMING_STORES (pixel stores as st.global.cs: 0.990 vs
+    # 0.992 ms per frame, e2e 1.194 vs 1.189), -DVXRT_EXP_WIDE_NOINLINE (the wide-block path as __noinline__ functions: one rank's
+    # share of 8 0.154 vs 0.144 ms)
 }
 
 

@@ -83,11 +83,23 @@ struct Outputs {
     // waits for the owner (pdl_wait: griddepcontrol.wait before this kernel's first global write); the last one lets the kernel that
     // publishes the rank's completion flag become resident early (pdl_trigger)
     int pdl_wait, pdl_trigger;
+    int wide_blocks;                    // frame_kernel: its first wide_blocks blocks render the wide_blocks / 2 heaviest tiles, two blocks each, with
+                                        // two threads per hit pixel (see shade_wide_*); 0: every block renders one tile
     int32_t* dbg_hit;                   // optional (VXRT_FLAG_DEBUG_OUTPUTS), raster layout
     uint16_t* dbg_steps;
     uint32_t* dbg_occl;
     uint32_t* dbg_cast;
 };
+
+// the pixel store.  VXRT_EXP_STREAMING_STORES (variant library, voxel-rt_b200/build.py): st.global.cs -- the 33 MB of a 4K frame are
+// written once and read by the copy engine, they need not displace the grid in L2
+__device__ __forceinline__ void store_pixel(uint32_t* p, uint32_t v) {
+#ifdef VXRT_EXP_STREAMING_STORES
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 
 __device__ __forceinline__ uint32_t out_index_of(const TileMap& m, int raster, int px, int py) {
     if (raster) return (uint32_t)(py * m.width + px);
@@ -137,11 +149,11 @@ __device__ __forceinline__ bool primary_pixel(const Grid& g, const FrameParams& 
         if (o.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");   // nothing is written before the kernel ahead has completed
         if (f.view_depth_field == 1) {                               // :143-145
             const float grey = __fdiv_rn((float)r.steps, 100.0f);
-            o.rgba8[out_index_of(m, o.raster, px, py)] = pack_rgba8(grey, grey, grey, 1.0f);
+            store_pixel(o.rgba8 + out_index_of(m, o.raster, px, py), pack_rgba8(grey, grey, grey, 1.0f));
         } else if (r.idx >= 0) {
             hit = true;                                              // lighting follows
         } else {
-            o.rgba8[out_index_of(m, o.raster, px, py)] = pack_rgba8(0.6f, 0.7f, 0.8f, 1.0f);   // :133
+            store_pixel(o.rgba8 + out_index_of(m, o.raster, px, py), pack_rgba8(0.6f, 0.7f, 0.8f, 1.0f));   // :133
         }
         if (o.dbg_hit) {
             o.dbg_hit[pid] = r.idx;
@@ -340,9 +352,102 @@ __device__ __forceinline__ void shade_pixel(const Grid& g, const FrameParams& f,
     const float cg = __fmul_rn(__fdiv_rn((float)((packed >> 8) & 255u), 255.0f), multiplier);
     const float cb = __fmul_rn(__fdiv_rn((float)(packed & 255u), 255.0f), multiplier);
     const int px = (int)(pid % (uint32_t)m.width), py = (int)(pid / (uint32_t)m.width);
-    o.rgba8[out_index_of(m, o.raster, px, py)] = pack_rgba8(cr, cg, cb, 1.0f);
+    store_pixel(o.rgba8 + out_index_of(m, o.raster, px, py), pack_rgba8(cr, cg, cb, 1.0f));
     if (o.dbg_occl) { o.dbg_occl[pid] = occl; o.dbg_cast[pid] = cast; }
 }
+// ---- wide blocks (frame_kernel; production variants only) --------------------------------------------------------------------
+// A small share of a frame lasts as long as its slowest block, and the slowest block is one tile whose pixels each walk all
+// 16 lights with long unobstructed rays: 1 + 16 rays in sequence per thread.  What a light ADDS to the multiplier
+// (fshader.glsl:166-179) does not depend on the multiplier, only whether the loop still runs does (:161-164), so the lights of a
+// pixel can be evaluated by two threads -- the second one speculatively, without the early-out -- and combined in slot order
+// afterwards: same additions, same order, same clamp tests.  The K heaviest tiles (previous frame's block times) are rendered
+// that way by two blocks each: a block takes half a tile (128 pixels); threads 0-127 trace the primary rays, the global shadow
+// ray and the first half of the active lights, threads 128-255 the second half of the lights of the same hit pixels.
+#ifdef VXRT_EXP_WIDE_NOINLINE           /* variant library: the wide path as functions of their own (register allocation apart from the kernel's) */
+#define VXRT_WIDE_FN __device__ __noinline__
+#else
+#define VXRT_WIDE_FN __device__ __forceinline__
+#endif
+struct WideShared {
+    float c[8][128];                    // [light of the second half][hit]: what it adds
+    unsigned char has[128];             // bit j: light j of the second half adds c[j]
+};
+// fshader.glsl:166-179 for one light and one hit pixel: true when the light adds c to the multiplier
+template <class Grid, bool TRAV>
+__device__ __forceinline__ bool light_term(const Grid& g, const float4 L, float hx, float hy, float hz, float nx, float ny, float nz,
+                                           bool skip_dark, float& c) {
+    float tx = __fsub_rn(L.x, hx), ty = __fsub_rn(L.y, hy), tz = __fsub_rn(L.z, hz);
+    const bool lit = dot3(nx, ny, nz, tx, ty, tz) > 0.0f || !(fabsf(L.w) <= 3.0e38f);
+    if (skip_dark && !lit) return false;
+    const float lld = __fsqrt_rn(dot3(tx, ty, tz, tx, ty, tz));                          // :168
+    if (!(lld <= (float)VXRT_LOCAL_LIGHT_DIST)) return false;                            // :171
+    normalize3_with_length(tx, ty, tz, lld);                                            // :173
+    const RayHit s = cast_ray<false, true, false, Grid, TRAV>(g, __fadd_rn(hx, __fmul_rn(tx, 0.001f)), __fadd_rn(hy, __fmul_rn(ty, 0.001f)),
+                              __fadd_rn(hz, __fmul_rn(tz, 0.001f)), tx, ty, tz, f2i(__fadd_rn(lld, 1.0f)));   // :175
+    if (s.idx != -1) return false;                                                      // :177
+    const float fall = __fmul_rn(__fsub_rn((float)VXRT_LOCAL_LIGHT_DIST, lld), 1.0f / (float)VXRT_LOCAL_LIGHT_DIST);
+    c = __fmul_rn(__fmul_rn(L.w, max0(dot3(nx, ny, nz, tx, ty, tz))), fall);
+    return true;
+}
+struct WideState { float multiplier; int last_slot; bool broke; };
+// before the barrier.  role 0: global shadow ray + lights [0, n0) in sequence (returns the loop's state); role 1: lights [n0, nactive)
+// without the early-out, into shared memory
+template <class Grid, bool TRAV>
+VXRT_WIDE_FN WideState shade_wide_first(const Grid& g, const FrameParams& f, const Outputs& o, const LightList& LL, const float4 rec,
+                                                      int role, int idx, WideShared& W) {
+    const uint32_t packed = __float_as_uint(rec.w);
+    float nx, ny, nz;
+    unpack_normal((int)(packed >> 24), nx, ny, nz);
+    const float hx = rec.x, hy = rec.y, hz = rec.z;
+    const bool skip_dark = o.skip_dark != 0;
+    const int nact = LL.nactive, n0 = nact >> 1;
+    WideState st = {VXRT_AMBIENT, -1, false};
+    if (role == 0) {
+        float lx = __fsub_rn(f.light_pos[0], hx), ly = __fsub_rn(f.light_pos[1], hy), lz = __fsub_rn(f.light_pos[2], hz);   // :147
+        if (dot3(nx, ny, nz, lx, ly, lz) > 0.0f || !skip_dark) {                        // :154
+            normalize3(lx, ly, lz);
+            const RayHit s = cast_ray<false, true, true, Grid, TRAV>(g, __fadd_rn(hx, __fmul_rn(lx, 0.001f)), __fadd_rn(hy, __fmul_rn(ly, 0.001f)),
+                                      __fadd_rn(hz, __fmul_rn(lz, 0.001f)), lx, ly, lz, VXRT_RENDER_DIST);
+            if (s.idx == -1) st.multiplier = __fadd_rn(st.multiplier, __fmul_rn(VXRT_DIFFUSE, max0(dot3(nx, ny, nz, lx, ly, lz))));   // :155
+        }
+        for (int k = 0; k < n0; k++) {
+            if (st.multiplier >= VXRT_MAX_OVERBRIGHT) { st.multiplier = VXRT_MAX_OVERBRIGHT; st.broke = true; break; }   // :161-164
+            st.last_slot = LL.slot[k];
+            float c;
+            if (light_term<Grid, TRAV>(g, LL.light[k], hx, hy, hz, nx, ny, nz, skip_dark, c)) st.multiplier = __fadd_rn(st.multiplier, c);
+        }
+    } else {
+        unsigned has = 0u;
+        for (int k = n0; k < nact; k++) {
+            float c = 0.0f;
+            if (light_term<Grid, TRAV>(g, LL.light[k], hx, hy, hz, nx, ny, nz, skip_dark, c)) has |= 1u << (k - n0);
+            W.c[k - n0][idx] = c;
+        }
+        W.has[idx] = (unsigned char)has;
+    }
+    return st;
+}
+// after the barrier, role 0: the second half's terms in slot order, with the clamp test in front of each; colour; store
+VXRT_WIDE_FN void shade_wide_second(const TileMap& m, const Outputs& o, const LightList& LL, const float4 rec, const uint32_t pid,
+                                                  WideState st, int idx, const WideShared& W) {
+    const uint32_t packed = __float_as_uint(rec.w);
+    const int nact = LL.nactive, n0 = nact >> 1;
+    if (!st.broke) {
+        const unsigned has = W.has[idx];
+        for (int k = n0; k < nact; k++) {
+            if (st.multiplier >= VXRT_MAX_OVERBRIGHT) { st.multiplier = VXRT_MAX_OVERBRIGHT; st.broke = true; break; }   // :161-164
+            st.last_slot = LL.slot[k];
+            if ((has >> (k - n0)) & 1u) st.multiplier = __fadd_rn(st.multiplier, W.c[k - n0][idx]);
+        }
+    }
+    if (!st.broke && st.last_slot < 15 && st.multiplier >= VXRT_MAX_OVERBRIGHT) st.multiplier = VXRT_MAX_OVERBRIGHT;
+    const float cr = __fmul_rn(__fdiv_rn((float)((packed >> 16) & 255u), 255.0f), st.multiplier);      // :184-187
+    const float cg = __fmul_rn(__fdiv_rn((float)((packed >> 8) & 255u), 255.0f), st.multiplier);
+    const float cb = __fmul_rn(__fdiv_rn((float)(packed & 255u), 255.0f), st.multiplier);
+    const int px = (int)(pid % (uint32_t)m.width), py = (int)(pid / (uint32_t)m.width);
+    store_pixel(o.rgba8 + out_index_of(m, o.raster, px, py), pack_rgba8(cr, cg, cb, 1.0f));
+}
+
 // block-level sums of the shade counters into the frame's counters (s_fetches / s_local: zeroed shared scratch; ends with a barrier)
 template <bool COUNT>
 __device__ __forceinline__ void shade_counts_to_global(const Outputs& o, const ShadeCounts& n, unsigned long long& s_fetches,
@@ -415,15 +520,22 @@ __global__ void __launch_bounds__(256, 5) frame_kernel(Grid g, const __grid_cons
     __shared__ unsigned int s_warp_hits[8];
     __shared__ unsigned int s_total;
     __shared__ unsigned long long s_fetches, s_local, s_fetches_primary;
+    __shared__ WideShared s_wide;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (o.pdl_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const long long t_start = clock64();
-    const int local_tile = o.tile_order ? (int)o.tile_order[blockIdx.x] : (int)blockIdx.x + m.tile_base;
+    // wide blocks (production variants): the first o.wide_blocks blocks take the heaviest tiles, two blocks per tile (shade_wide_*)
+    const bool wide = !COUNT && (int)blockIdx.x < o.wide_blocks;
+    const int pos = wide ? (int)(blockIdx.x >> 1) : (int)blockIdx.x - (COUNT ? 0 : (o.wide_blocks >> 1));
+    const int local_tile = o.tile_order ? (int)o.tile_order[pos] : pos + m.tile_base;
     compact_lights(f, s_lights, tid, lane);
     if (tid == 0) { s_fetches = 0ull; s_local = 0ull; s_fetches_primary = 0ull; }
     RayHit r;
-    uint32_t pid;
-    const bool hit = primary_pixel<COUNT, Grid, TRAV>(g, f, m, o, local_tile, warp, lane, r, pid);
+    uint32_t pid = 0u;
+    bool hit = false;
+    if (!wide) hit = primary_pixel<COUNT, Grid, TRAV>(g, f, m, o, local_tile, warp, lane, r, pid);
+    else if (warp < 4) hit = primary_pixel<COUNT, Grid, TRAV>(g, f, m, o, local_tile, (int)(blockIdx.x & 1u) * 4 + warp, lane, r, pid);
+    else { r.steps = 0; r.idx = -1; }                                // (the second half's threads join for the lights)
     if (o.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");       // (threads without a pixel have not waited yet)
     const unsigned ballot = __ballot_sync(0xffffffffu, hit);
     const unsigned wfetch = __reduce_add_sync(0xffffffffu, (unsigned)r.steps);
@@ -447,9 +559,20 @@ __global__ void __launch_bounds__(256, 5) frame_kernel(Grid g, const __grid_cons
     __syncthreads();
     if (tid == 0 && s_fetches_primary) atomicAdd(&o.counters->fetches_primary, s_fetches_primary);
     ShadeCounts n = {0u, 0u, 0u, 0u};
-    if (f.view_depth_field != 1 && (unsigned)tid < s_total) shade_pixel<COUNT, Grid, TRAV>(g, f, m, o, s_lights, s_hit[tid], s_pix[tid], n);
+    if (wide) {
+        if (!COUNT) {                                                // (never taken by the counted variants: wide is false there)
+            const int idx = tid & 127, role = tid >> 7;
+            const bool work = f.view_depth_field != 1 && (unsigned)idx < s_total;
+            WideState st = {VXRT_AMBIENT, -1, false};
+            if (work) st = shade_wide_first<Grid, TRAV>(g, f, o, s_lights, s_hit[idx], role, idx, s_wide);
+            __syncthreads();
+            if (work && role == 0) shade_wide_second(m, o, s_lights, s_hit[idx], s_pix[idx], st, idx, s_wide);
+        }
+    } else if (f.view_depth_field != 1 && (unsigned)tid < s_total) shade_pixel<COUNT, Grid, TRAV>(g, f, m, o, s_lights, s_hit[tid], s_pix[tid], n);
     shade_counts_to_global<COUNT>(o, n, s_fetches, s_local, tid, lane);
-    if (tid == 0 && o.tile_cost) o.tile_cost[local_tile] = (uint32_t)min((long long)0xffffffffll, clock64() - t_start);
+    // (a wide block records twice its time, and only the first half does: what the tile would cost one block keeps it among the heaviest)
+    if (tid == 0 && o.tile_cost && (!wide || (blockIdx.x & 1u) == 0u))
+        o.tile_cost[local_tile] = (uint32_t)min((long long)0xffffffffll, (clock64() - t_start) * (wide ? 2 : 1));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -624,6 +747,18 @@ __global__ void division_selftest_kernel(unsigned long long n, unsigned long lon
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// self-test of the step reciprocals (ray.cuh cast_ray, :74-76): refined_rcp(b) against IEEE rcp.rn(b) for EVERY float b in
+// [2^-40, 4) -- 42 binades x 2^23 mantissas (the kernels use it for b = |dir + 0.000001| in [2^-40, 2.000001])
+__global__ void reciprocal_selftest_kernel(unsigned long long* mismatches) {
+    const unsigned long long n = 42ull << 23, stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float b = __uint_as_float(((unsigned)(127 - 40) << 23) + (unsigned)i);       // consecutive bit patterns from 2^-40 up
+        if (__float_as_uint(refined_rcp(b)) != __float_as_uint(__frcp_rn(b))) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // ---- peer-memory frame target (multi-GPU without a gather) -----------------------------------------
 // The display rank owns {2 raster frames, done[world] flags, consumed counter}; every rank's kernels store their
 // pixels straight into the owner's frame over NVLink, then publish completion with a system-scope release; the
@@ -678,11 +813,13 @@ __global__ void p2p_signal_done_kernel(P2PShared* sh, int rank, unsigned long lo
 }
 // owner: all ranks have written frame `seq`
 __global__ void p2p_wait_done_kernel(const P2PShared* sh, int world, unsigned long long seq, int* err) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");    // (a release queued right behind may become resident now)
     const int r = threadIdx.x;
     if (r < world && !spin_until(&sh->done[16 * r], seq + 1)) *err = 2;
 }
 // owner: frame `seq` consumed
 __global__ void p2p_release_kernel(P2PShared* sh, unsigned long long seq) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");                 // no-op unless launched with programmatic stream serialization
     __threadfence_system();
     st_release_sys(&sh->consumed, seq + 1);
 }

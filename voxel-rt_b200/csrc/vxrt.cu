@@ -102,6 +102,7 @@ struct vxrt_ctx {
     uint32_t frame_seq = 0;
     bool last_fused = false;            // the last frame ran as one fused kernel
     bool row_partition = false;         // vxrt_set_partition: whole tile rows are the interleaved unit
+    int wide_tiles = 8;                 // vxrt_set_wide_tiles: how many of the heaviest tiles of a fused frame get two blocks / two threads per hit pixel
     bool use_culling = true;
     int l2_prefetch = 2;                // vxrt_set_l2_prefetch: 0 off, 1 on, 2 auto (on when this context renders <= 12,000 tiles)
     int shade_threads = 128;            // threads per shade block (VXRT_SHADE_THREADS: 64 / 128 / 256; 128 measured best)
@@ -433,6 +434,7 @@ extern "C" int vxrt_create(const vxrt_config* cfg, vxrt_ctx** out) {
     if (const char* e = getenv("VXRT_OVERLAP")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->overlap = v; }
     if (const char* e = getenv("VXRT_FUSION")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->fusion = v; }
     if (const char* e = getenv("VXRT_P2P_PDL")) c->p2p_pdl = atoi(e) != 0;
+    if (const char* e = getenv("VXRT_WIDE_TILES")) { const int v = atoi(e); if (v >= 0 && v <= 64) c->wide_tiles = v; }
     if (const char* e = getenv("VXRT_SHADE_THREADS")) {
         const int v = atoi(e);
         if (v == 64 || v == 128 || v == 256) c->shade_threads = v;
@@ -1096,12 +1098,18 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         o.tile_ready = c->d_tile_ready; o.overlap_err = c->d_overlap_err;
         o.frame_seq = ++c->frame_seq;
         c->last_fused = fused;
-        o.pdl_wait = 0; o.pdl_trigger = 0;
+        o.pdl_wait = 0; o.pdl_trigger = 0; o.wide_blocks = 0;
         const bool shade_follows = !fused && c->frame.view_depth_field != 1;
         if (fused) {
             // one kernel per frame: each block traces its tile's primary rays and then shades its own hits (kernels.cuh frame_kernel)
             o.pdl_wait = pdl_first ? 1 : 0; o.pdl_trigger = pdl_chain ? 1 : 0;
-            VXRT_LAUNCH(frame_kernel, count_primary, trav_primary, grid, block, pdl_first);
+            // wide blocks: the heaviest tiles (the head of the launch order) are rendered by two blocks each, two threads per hit
+            // pixel (kernels.cuh shade_wide_*); production variants of the lit view only
+            int nwide = 0;
+            if (!count_primary && o.tile_order && c->wide_tiles > 0) nwide = std::min(c->wide_tiles, ntile / 8);
+            o.wide_blocks = 2 * nwide;
+            const dim3 fgrid((unsigned)(ntile + nwide));
+            VXRT_LAUNCH(frame_kernel, count_primary, trav_primary, fgrid, block, pdl_first);
             CUDA_TRY(cudaGetLastError());
             c->launches++;
             pdl_first = false;
@@ -1244,6 +1252,13 @@ extern "C" int vxrt_set_partition(vxrt_ctx* c, int mode) {
     CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
     c->row_partition = mode == 1;
     return alloc_frame_buffers(c);       // other local tiles: hit slots, launch orders and the local frame start over
+}
+
+extern "C" int vxrt_set_wide_tiles(vxrt_ctx* c, int tiles) {
+    CHECK_CTX(c);
+    if (tiles < 0 || tiles > 64) return fail(VXRT_ERR_INVALID, "set_wide_tiles: 0 (off) .. 64");
+    c->wide_tiles = tiles;
+    return VXRT_OK;
 }
 
 extern "C" int vxrt_frame_was_fused(vxrt_ctx* c) { return (c && c->last_fused) ? 1 : 0; }
@@ -1458,6 +1473,23 @@ extern "C" int vxrt_selftest_division(vxrt_ctx* c, uint64_t n, uint64_t seed, ui
     return VXRT_OK;
 }
 
+extern "C" int vxrt_selftest_reciprocal(vxrt_ctx* c, uint64_t* mismatches) {
+    CHECK_CTX(c);
+    if (!mismatches) return fail(VXRT_ERR_INVALID, "selftest_reciprocal: null output");
+    unsigned long long* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 8));
+    cudaMemsetAsync(d, 0, 8, c->stream);
+    reciprocal_selftest_kernel<<<148 * 8, 256, 0, c->stream>>>(d);
+    unsigned long long h = 0;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(VXRT_ERR_CUDA, std::string("selftest_reciprocal: ") + cudaGetErrorString(e));
+    *mismatches = h;
+    return VXRT_OK;
+}
+
 extern "C" int vxrt_write_ppm(vxrt_ctx* c, const char* path) {
     CHECK_CTX(c);
     if (!path) return fail(VXRT_ERR_INVALID, "write_ppm: null path");
@@ -1580,7 +1612,17 @@ extern "C" int vxrt_p2p_release_frame(vxrt_ctx* c) {
     CHECK_CTX(c);
     if (!c->p2p || !c->p2p_owner) return fail(VXRT_ERR_STATE, "p2p_release_frame: not the owner of a peer-memory target");
     if (c->p2p_seq == 0) return fail(VXRT_ERR_STATE, "p2p_release_frame before render");
-    p2p_release_kernel<<<1, 1, 0, c->stream>>>((P2PShared*)c->p2p_base, c->p2p_seq - 1);
+    {   // programmatic stream serialization: behind p2p_wait_done_kernel (or the consumer's last kernel) the release is resident
+        // before that kernel ends; it waits for its completion (griddepcontrol.wait) before it publishes
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof lc);
+        lc.gridDim = dim3(1); lc.blockDim = dim3(1); lc.stream = c->stream;
+        cudaLaunchAttribute la[1];
+        la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        la[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = la; lc.numAttrs = c->p2p_pdl ? 1 : 0;
+        CUDA_TRY(cudaLaunchKernelEx(&lc, p2p_release_kernel, (P2PShared*)c->p2p_base, c->p2p_seq - 1));
+    }
     CUDA_TRY(cudaGetLastError());
     return VXRT_OK;
 }
