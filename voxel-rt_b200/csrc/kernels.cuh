@@ -799,15 +799,21 @@ __global__ void p2p_wait_consumed_kernel(const P2PShared* sh, unsigned long long
 // blocks start at once (launch_dependents below) and trace their primary rays while this one still waits; they execute
 // griddepcontrol.wait -- this grid completed, its writes visible -- before their first global write.  Also zeroes the frame's
 // counters (instead of a memset node in the stream).  One block of 64 threads.
-__global__ void __launch_bounds__(64) p2p_begin_kernel(const P2PShared* sh, unsigned long long seq, int* err, unsigned int* counters, int nwords) {
+__global__ void __launch_bounds__(64) p2p_begin_kernel(const P2PShared* sh, unsigned long long seq, int* err, unsigned int* counters, int nwords,
+                                                       unsigned long long* chain_time) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0 && chain_time) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(chain_time[0]));   // the frame's chain starts (vxrt_get_stats)
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) counters[i] = 0u;
     if (threadIdx.x == 0 && seq >= 2 && !spin_until(&sh->consumed, seq - 1)) *err = 1;
 }
 // all ranks, after rendering frame `seq` (griddepcontrol.wait: no-op unless launched with programmatic stream serialization, where
 // it returns once the render kernel ahead has completed and its stores -- the pixels in the owner's frame -- are performed)
-__global__ void p2p_signal_done_kernel(P2PShared* sh, int rank, unsigned long long seq) {
+__global__ void p2p_signal_done_kernel(P2PShared* sh, int rank, unsigned long long seq, unsigned long long* chain_time) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");    // (the owner's wait / release may become resident behind this one)
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // the frame's chain ends here: the stream carries no event records between the chain's kernels (they would break the programmatic
+    // dependencies), the times come from the device's clock instead
+    if (chain_time) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(chain_time[1]));
     __threadfence_system();
     st_release_sys(&sh->done[16 * rank], seq + 1);
 }

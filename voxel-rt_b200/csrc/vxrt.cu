@@ -127,6 +127,8 @@ struct vxrt_ctx {
     size_t p2p_frame_bytes = 0;
     unsigned long long p2p_seq = 0;     // frames rendered into the target so far
     int* d_p2p_err = nullptr;
+    unsigned long long* d_chain_time = nullptr;   // [2]: globaltimer at the start / end of a programmatically chained frame
+    bool chain_timed = false, chain_has_ev1 = false;
     bool p2p_begin_overlap = false;     // the frame's first render kernel may start while p2p_begin_kernel waits (importers on another device only)
     bool p2p_pdl = true;                // flag protocol chained with programmatic dependent launches (VXRT_P2P_PDL=0: separate plain launches)
     int stats_mode = 0;                 // vxrt_set_stats: 0 = production kernels (no per-iteration counters); 1 = counted variants, every ray
@@ -451,6 +453,7 @@ extern "C" void vxrt_destroy(vxrt_ctx* c) {
     free_frame_buffers(c);
     if (c->p2p_base) { if (c->p2p_owner) cudaFree(c->p2p_base); else if (!c->p2p_attached) cudaIpcCloseMemHandle(c->p2p_base); }
     cudaFree(c->d_p2p_err);
+    cudaFree(c->d_chain_time);
     cudaFree(c->d_overlap_err);
     cudaFree(c->d_yrange);
     cudaFree(c->d_vox); cudaFree(c->d_trav); cudaFree(c->d_trav_bad); cudaFree(c->d_counters); cudaFree(c->d_stage); cudaFree(c->d_first);
@@ -1001,7 +1004,7 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
     if (pdl_chain) {
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         p2p_begin_kernel<<<1, 64, 0, c->stream>>>((const P2PShared*)c->p2p_base, c->p2p_seq, c->d_p2p_err, (unsigned int*)c->d_counters,
-                                                  (int)(sizeof(Counters) * MAX_BANDS / sizeof(unsigned int)));
+                                                  (int)(sizeof(Counters) * MAX_BANDS / sizeof(unsigned int)), c->d_chain_time);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
     } else {
@@ -1162,18 +1165,20 @@ static int render_bands(vxrt_ctx* c, int nbands, uint8_t* host_dst, uint32_t* de
         la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         la[0].val.programmaticStreamSerializationAllowed = 1;
         lc.attrs = la; lc.numAttrs = 1;
-        CUDA_TRY(cudaLaunchKernelEx(&lc, p2p_signal_done_kernel, (P2PShared*)c->p2p_base, (int)c->cfg.rank, c->p2p_seq));
+        CUDA_TRY(cudaLaunchKernelEx(&lc, p2p_signal_done_kernel, (P2PShared*)c->p2p_base, (int)c->cfg.rank, c->p2p_seq, c->d_chain_time));
         c->launches++;
         c->p2p_seq++;
-        if (!ev1_recorded) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));   // (one render kernel: ms_primary reads as the whole frame)
-        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        // no event records behind the chain: the owner's wait / release kernels (vxrt_p2p_wait_frame / _release_frame) chain on
+        // programmatically as well; vxrt_get_stats takes the chain's span from the device clock (d_chain_time)
+        c->chain_timed = true; c->chain_has_ev1 = ev1_recorded;
         if (nbands == 1 && c->use_tile_order) c->order_frame++;
     } else {
+    c->chain_timed = false;
     if (nbands != 1) CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
     if (nbands == 1 && c->use_tile_order) c->order_frame++;
     if (p2p_frame) {
-        p2p_signal_done_kernel<<<1, 1, 0, c->stream>>>((P2PShared*)c->p2p_base, c->cfg.rank, c->p2p_seq);
+        p2p_signal_done_kernel<<<1, 1, 0, c->stream>>>((P2PShared*)c->p2p_base, c->cfg.rank, c->p2p_seq, (unsigned long long*)nullptr);
         CUDA_TRY(cudaGetLastError());
         c->launches++;
         c->p2p_seq++;
@@ -1405,9 +1410,21 @@ extern "C" int vxrt_get_stats(vxrt_ctx* c, vxrt_stats* out) {
     out->fetches = h.fetches_primary + h.fetches_shadow;
     out->fetches_primary = h.fetches_primary;
     out->rays_dark = h.rays_dark;
-    CUDA_TRY(cudaEventElapsedTime(&out->ms_primary, c->ev[0], c->ev[1]));
-    CUDA_TRY(cudaEventElapsedTime(&out->ms_shadow, c->ev[1], c->ev[2]));
-    CUDA_TRY(cudaEventElapsedTime(&out->ms_total, c->ev[0], c->ev[2]));
+    if (c->chain_timed) {
+        // a peer-memory frame whose kernels are chained programmatically: the chain's span from the device clock (globaltimer, ns)
+        unsigned long long tt[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(tt, c->d_chain_time, sizeof tt, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        out->ms_total = (tt[1] > tt[0]) ? (float)((double)(tt[1] - tt[0]) * 1e-6) : 0.0f;
+        if (c->chain_has_ev1) { CUDA_TRY(cudaEventElapsedTime(&out->ms_primary, c->ev[0], c->ev[1])); }   // two passes: an event sits between them
+        else out->ms_primary = out->ms_total;
+        if (out->ms_primary > out->ms_total) out->ms_primary = out->ms_total;
+        out->ms_shadow = out->ms_total - out->ms_primary;
+    } else {
+        CUDA_TRY(cudaEventElapsedTime(&out->ms_primary, c->ev[0], c->ev[1]));
+        CUDA_TRY(cudaEventElapsedTime(&out->ms_shadow, c->ev[1], c->ev[2]));
+        CUDA_TRY(cudaEventElapsedTime(&out->ms_total, c->ev[0], c->ev[2]));
+    }
     out->kernel_launches = c->launches;
     return VXRT_OK;
 }
@@ -1540,6 +1557,8 @@ extern "C" int vxrt_p2p_export(vxrt_ctx* c, uint8_t handle[64]) {
     }
     CUDA_TRY(cudaMalloc(&c->d_p2p_err, sizeof(int)));
     CUDA_TRY(cudaMemset(c->d_p2p_err, 0, sizeof(int)));
+    CUDA_TRY(cudaMalloc(&c->d_chain_time, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(c->d_chain_time, 0, 2 * sizeof(unsigned long long)));
     cudaIpcMemHandle_t h;
     CUDA_TRY(cudaIpcGetMemHandle(&h, c->p2p_base));
     memcpy(handle, &h, 64);
@@ -1578,6 +1597,8 @@ extern "C" int vxrt_p2p_import(vxrt_ctx* c, const uint8_t handle[64]) {
     c->p2p_frame_bytes = (size_t)c->cfg.width * c->cfg.height * 4;
     CUDA_TRY(cudaMalloc(&c->d_p2p_err, sizeof(int)));
     CUDA_TRY(cudaMemset(c->d_p2p_err, 0, sizeof(int)));
+    CUDA_TRY(cudaMalloc(&c->d_chain_time, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(c->d_chain_time, 0, 2 * sizeof(unsigned long long)));
     c->p2p = true; c->p2p_owner = false; c->p2p_seq = 0;
     return VXRT_OK;
 }
@@ -1592,6 +1613,8 @@ extern "C" int vxrt_p2p_attach(vxrt_ctx* c, void* owner_base) {
     c->p2p_frame_bytes = (size_t)c->cfg.width * c->cfg.height * 4;
     CUDA_TRY(cudaMalloc(&c->d_p2p_err, sizeof(int)));
     CUDA_TRY(cudaMemset(c->d_p2p_err, 0, sizeof(int)));
+    CUDA_TRY(cudaMalloc(&c->d_chain_time, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(c->d_chain_time, 0, 2 * sizeof(unsigned long long)));
     c->p2p = true; c->p2p_owner = false; c->p2p_attached = true; c->p2p_seq = 0;
     return VXRT_OK;
 }
@@ -1602,8 +1625,18 @@ extern "C" int vxrt_p2p_wait_frame(vxrt_ctx* c, void** frame) {
     if (!c->p2p || !c->p2p_owner) return fail(VXRT_ERR_STATE, "p2p_wait_frame: not the owner of a peer-memory target");
     if (c->p2p_seq == 0) return fail(VXRT_ERR_STATE, "p2p_wait_frame before render");
     const unsigned long long seq = c->p2p_seq - 1;
-    p2p_wait_done_kernel<<<1, 32, 0, c->stream>>>((const P2PShared*)c->p2p_base, c->cfg.world, seq, c->d_p2p_err);
-    CUDA_TRY(cudaGetLastError());
+    {   // programmatic stream serialization: directly behind this rank's own p2p_signal_done_kernel the wait is resident (and already
+        // polling the other ranks' flags) before the frame's kernels end; it completes only when every flag -- this rank's included --
+        // is there, and the release queued behind it waits for that completion
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof lc);
+        lc.gridDim = dim3(1); lc.blockDim = dim3(32); lc.stream = c->stream;
+        cudaLaunchAttribute la[1];
+        la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        la[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = la; lc.numAttrs = c->p2p_pdl ? 1 : 0;
+        CUDA_TRY(cudaLaunchKernelEx(&lc, p2p_wait_done_kernel, (const P2PShared*)c->p2p_base, (int)c->cfg.world, seq, c->d_p2p_err));
+    }
     if (frame) *frame = c->p2p_base + sizeof(P2PShared) + (seq & 1) * c->p2p_frame_bytes;
     return VXRT_OK;
 }
