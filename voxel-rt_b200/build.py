@@ -101,8 +101,10 @@ VARIANTS = {
     # default library stays exactly what was validated (VXRT_LIB=... pytest -m gpu runs the whole parity suite on one;
     # bench.py's "experiments" object times every entry).  Round 1's late_domain_check is the default now, jump_prefetch
     # (a measured loss) is gone.
-    "early_domain_check": ["-DVXRT_EARLY_DOMAIN_CHECK"],    # test the fast domain of a jump's re-base before dividing (ray.cuh; round 1's order)
-    "early_check_primary": ["-DVXRT_EARLY_DOMAIN_CHECK_PRIMARY"],   # ... in the compiler-scheduled loop (primary rays) only
+    # The order of "divide" and "test the fast domain" in a jump's re-base (ray.cuh) is chosen per kernel: test first in the stand-alone
+    # primary kernel, divide first everywhere else.  The two uniform orders stay as variants:
+    "early_domain_check": ["-DVXRT_EARLY_DOMAIN_CHECK"],    # test first everywhere (round 1's order)
+    "late_domain_check": ["-DVXRT_LATE_DOMAIN_CHECK"],      # divide first everywhere (round 2's order until call 19)
     # measured and dropped (round 2, call 15; the macros remain): -DVXRT_EXP_STREAMING_STORES (pixel stores as st.global.cs: 0.990 vs
     # 0.992 ms per frame, e2e 1.194 vs 1.189), -DVXRT_EXP_WIDE_NOINLINE (the wide-block path as __noinline__ functions: one rank's
     # share of 8 0.154 vs 0.144 ms)

@@ -116,7 +116,7 @@ __device__ __forceinline__ uint32_t out_index_of(const TileMap& m, int raster, i
 
 // fshader.glsl:131-145 for the pixel of this thread: ray set-up, primary castRay, misses / the step-count view finished here.
 // Returns true when the pixel hit a voxel (its lighting follows, fshader.glsl:147-187).
-template <bool COUNT, class Grid, bool TRAV>
+template <bool COUNT, class Grid, bool TRAV, bool EARLY = false>
 __device__ __forceinline__ bool primary_pixel(const Grid& g, const FrameParams& f, const TileMap& m, const Outputs& o, int local_tile,
                                               int warp, int lane, RayHit& r, uint32_t& pid) {
     const int lx = (warp & 3) * 8 + (lane & 7), ly = (warp >> 2) * 4 + (lane >> 3);
@@ -145,7 +145,7 @@ __device__ __forceinline__ bool primary_pixel(const Grid& g, const FrameParams& 
         const float rx = __fadd_rn(__fadd_rn(__fmul_rn(M[0], dxn), __fmul_rn(M[4], dyn)), __fadd_rn(__fmul_rn(M[8], dzn), __fmul_rn(M[12], 0.0f)));
         const float ry = __fadd_rn(__fadd_rn(__fmul_rn(M[1], dxn), __fmul_rn(M[5], dyn)), __fadd_rn(__fmul_rn(M[9], dzn), __fmul_rn(M[13], 0.0f)));
         const float rz = __fadd_rn(__fadd_rn(__fmul_rn(M[2], dxn), __fmul_rn(M[6], dyn)), __fadd_rn(__fmul_rn(M[10], dzn), __fmul_rn(M[14], 0.0f)));
-        r = cast_ray<COUNT, false, true, Grid, TRAV>(g, f.cam_pos[0], f.cam_pos[1], f.cam_pos[2], rx, ry, rz, VXRT_RENDER_DIST);   // :139
+        r = cast_ray<COUNT, false, true, Grid, TRAV, EARLY>(g, f.cam_pos[0], f.cam_pos[1], f.cam_pos[2], rx, ry, rz, VXRT_RENDER_DIST);   // :139
         if (o.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");   // nothing is written before the kernel ahead has completed
         if (f.view_depth_field == 1) {                               // :143-145
             const float grey = __fdiv_rn((float)r.steps, 100.0f);
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256, 6) primary_kernel(Grid g, const __grid_co
     const int local_tile = o.tile_order ? (int)o.tile_order[blockIdx.x] : (int)blockIdx.x + m.tile_base;
     RayHit r;
     uint32_t pid;
-    const bool hit = primary_pixel<COUNT, Grid, TRAV>(g, f, m, o, local_tile, warp, lane, r, pid);
+    const bool hit = primary_pixel<COUNT, Grid, TRAV, true>(g, f, m, o, local_tile, warp, lane, r, pid);   // (EARLY: ray.cuh cast_ray)
     if (o.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");       // (threads without a pixel have not waited yet)
     // ---- hit compaction into the tile's 256 slots: warp ballot -> block prefix (no global ordering: the shade pass
     //      schedules tiles by its own cost feedback) ---------------------------------------------------------------
