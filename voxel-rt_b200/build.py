@@ -99,8 +99,7 @@ def build(force=False, verbose=False):
 VARIANTS = {
     # name -> extra nvcc flags; experiments that change the SASS of the render kernels live behind macros so that the
     # default library stays exactly what was validated (VXRT_LIB=... pytest -m gpu runs the whole parity suite on one;
-    # bench.py's "experiments" object times every entry).  Round 1's late_domain_check is the default now, jump_prefetch
-    # (a measured loss) is gone.
+    # bench.py's "experiments" object times every entry).
     # The order of "divide" and "test the fast domain" in a jump's re-base (ray.cuh) is chosen per kernel: test first in the stand-alone
     # primary kernel, divide first everywhere else.  The two uniform orders stay as variants:
     "early_domain_check": ["-DVXRT_EARLY_DOMAIN_CHECK"],    # test first everywhere (round 1's order)
