@@ -1769,8 +1769,14 @@ extern "C" int vxrt_render_to_host_frame(vxrt_ctx* c, const vxrt_frame* f, vxrt_
     if (hf->width != c->cfg.width || hf->height != c->cfg.height) return fail(VXRT_ERR_INVALID, "render_to_host_frame: the host frame has other extents than the context");
     if (c->cfg.rank >= 64) return fail(VXRT_ERR_INVALID, "render_to_host_frame: at most 64 ranks");
     HostFrameFlags* fl = host_frame_flags(hf);
-    // the previous frame of THIS host frame must have been released by the display rank before it is overwritten
-    if (seq > 1 && !host_spin_until(&fl->released, seq - 1, 4000)) return fail(VXRT_ERR_STATE, "render_to_host_frame: the display rank did not release the previous frame (4 s)");
+    // the previous frame of THIS host frame must have been released by the display rank before it is overwritten: before the
+    // kernels are launched when they store into the host frame themselves, before the COPY is queued when they render into a local
+    // buffer first (tile-row partition: the kernels of this frame then run while the display rank still holds the frame before last)
+    auto wait_released = [&]() -> int {
+        if (seq > 1 && !host_spin_until(&fl->released, seq - 1, 4000))
+            return fail(VXRT_ERR_STATE, "render_to_host_frame: the display rank did not release the previous frame (4 s)");
+        return VXRT_OK;
+    };
     void* dpix = nullptr;
     CUDA_TRY(cudaHostGetDevicePointer(&dpix, hf->base, 0));
     unsigned long long* dflag = (unsigned long long*)((uint8_t*)dpix + ((uint8_t*)&fl->done[c->cfg.rank] - hf->base));
@@ -1788,6 +1794,8 @@ extern "C" int vxrt_render_to_host_frame(vxrt_ctx* c, const vxrt_frame* f, vxrt_
         if (rc != VXRT_OK) return rc;
         CUDA_TRY(cudaEventRecord(c->ev_band[0], c->stream));
         CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_band[0], 0));
+        rc = wait_released();                               // (the kernels are already running)
+        if (rc != VXRT_OK) return rc;
         const int W = c->cfg.width, H = c->cfg.height, world = c->cfg.world, rank = c->cfg.rank;
         const size_t strip = (size_t)W * TILE_H * 4;
         const int my_rows = (c->map.ty > rank) ? (c->map.ty - rank + world - 1) / world : 0;      // tile rows rank, rank + world, ...
@@ -1810,6 +1818,8 @@ extern "C" int vxrt_render_to_host_frame(vxrt_ctx* c, const vxrt_frame* f, vxrt_
         c->submit_seq++;
         return VXRT_OK;
     }
+    rc = wait_released();
+    if (rc != VXRT_OK) return rc;
     rc = render_bands(c, 1, nullptr, (uint32_t*)dpix, /*fence_main=*/true, /*raster_out=*/true);
     if (rc != VXRT_OK) return rc;
     host_flag_kernel<<<1, 1, 0, c->stream>>>(dflag, (unsigned long long)seq);
