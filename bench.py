@@ -7,11 +7,16 @@
     python bench.py --impl reference ...     # the reference's own shader on the host CPU cores
 
 A "step" is one frame: the per-pixel path (primary DDA + shadow/light rays + shading) over every pixel of
-the frame.  Rays are counted by the REFERENCE's casting rule: W*H primary rays, one global-light
-ray per hit pixel, one local-light ray per (hit pixel, light) the reference shader would cast.
-N > 1: sort-first image-tile split (groups of N consecutive tiles dealt one to each rank, rotated per tile row), grid replicated, one NCCL all-gather of the RGBA8
-tiles per frame + an un-tile kernel on every rank; total work is fixed => "scaling": "strong".
+the frame.  `value` counts the rays the timed kernels actually trace (primary + lit global + lit local); the same time by the
+REFERENCE's casting rule (W*H primary rays, one global-light ray per hit pixel, one local-light ray per (hit
+pixel, light) the reference shader would cast) and with every reference ray marched to its end are printed beside it.
+N > 1: sort-first image-tile split (groups of N consecutive tiles dealt one to each rank, rotated per tile row), grid
+replicated; the ranks' kernels store their pixels straight into rank 0's frame over NVLink peer memory (--exchange nccl: one
+all-gather of the RGBA8 tiles per frame + an un-tile kernel); total work is fixed => "scaling": "strong".  e2e: the frame in
+rank 0's HOST memory every step (N = 1 pipelined read-back; N = 2 peer memory + one read-back; N >= 4 tile-row partition, every
+rank moves its strips into one shared page-locked host frame by DMA).
 --partition frames (opt-in): whole frames are the sharded unit instead (frame f on rank f % N, nothing exchanged) => "weak".
+Every line carries "parity": the frame the timed public call delivered against the oracle (checker only, after all timing).
 
 Prints ONE JSON line (rank 0).
 """
