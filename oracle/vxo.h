@@ -145,4 +145,9 @@ void vxo_trav_render(const int32_t* trav, vxo_dims g, const vxo_frame* f, int wi
 #ifdef __cplusplus
 }
 #endif
+/* ---- host statement of how the CUDA path's production kernels organise the lighting (vxo_wide.c; test infrastructure) ----
+ * skip_dark: rays toward lights the surface faces away from are not traced; wide: the active lights are evaluated in two halves,
+ * the second without the early-out, and combined in slot order.  Must equal vxo_render's float frame bit for bit. */
+void vxo_wide_render(const int32_t* vox, vxo_dims g, const vxo_frame* f, int width, int height, int skip_dark, int wide, float* rgba_f32);
+
 #endif

@@ -193,6 +193,17 @@ class Oracle:
         return out
 
 
+    # ---- host statement of the production kernels' lighting (oracle/vxo_wide.c) ----
+    def wide_render(self, vox, dims, frame, width, height, skip_dark, wide):
+        """float RGBA frame with the lighting organised like the CUDA path's production kernels (active lights compacted, unlit rays
+        skipped, the two-halves evaluation of the wide blocks)"""
+        out = np.zeros((height, width, 4), np.float32)
+        self.L.vxo_wide_render.restype = None
+        self.L.vxo_wide_render(_ptr(vox, C.c_int32), Dims(*dims), C.byref(frame), C.c_int(width), C.c_int(height),
+                               C.c_int(1 if skip_dark else 0), C.c_int(1 if wide else 0), _ptr(out, C.c_float))
+        return out
+
+
 def ref_available():
     return all(os.path.exists(os.path.join(REF_DIR, f)) for f in ("libref_host.so", "libref_shader.so"))
 
