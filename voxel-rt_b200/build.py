@@ -99,14 +99,16 @@ def build(force=False, verbose=False):
 VARIANTS = {
     # name -> extra nvcc flags; experiments that change the SASS of the render kernels live behind macros so that the
     # default library stays exactly what was validated (VXRT_LIB=... pytest -m gpu runs the whole parity suite on one;
-    # bench.py's "experiments" object times every entry).
-    # The order of "divide" and "test the fast domain" in a jump's re-base (ray.cuh) is chosen per kernel: test first in the stand-alone
-    # primary kernel, divide first everywhere else.  The two uniform orders stay as variants:
-    "early_domain_check": ["-DVXRT_EARLY_DOMAIN_CHECK"],    # test first everywhere (round 1's order)
-    "late_domain_check": ["-DVXRT_LATE_DOMAIN_CHECK"],      # divide first everywhere (round 2's order until call 19)
-    # measured and dropped (round 2, call 15; the macros remain): -DVXRT_EXP_STREAMING_STORES (pixel stores as st.global.cs: 0.990 vs
-    # 0.992 ms per frame, e2e 1.194 vs 1.189), -DVXRT_EXP_WIDE_NOINLINE (the wide-block path as __noinline__ functions: one rank's
-    # share of 8 0.154 vs 0.144 ms)
+    # bench.py's "experiments" object times every entry).  Nothing is open at the end of round 2.
+}
+CLOSED_VARIANTS = {
+    # measured and decided (profiles/r2_final_bench_1gpu.json, r2_call15_bench_1gpu.json); still buildable by name:
+    # The order of "divide" and "test the fast domain" in a jump's re-base (ray.cuh) is chosen per kernel: test first in the
+    # stand-alone primary kernel, divide first everywhere else.  The two uniform orders:
+    "early_domain_check": ["-DVXRT_EARLY_DOMAIN_CHECK"],    # test first everywhere (round 1's order): shade pass 0.728 vs 0.709 ms
+    "late_domain_check": ["-DVXRT_LATE_DOMAIN_CHECK"],      # divide first everywhere: primary pass 0.284 vs 0.275 ms
+    "streaming_stores": ["-DVXRT_EXP_STREAMING_STORES"],    # pixel stores as st.global.cs: 0.990 vs 0.992 ms per frame, e2e 1.194 vs 1.189
+    "wide_noinline": ["-DVXRT_EXP_WIDE_NOINLINE"],          # the wide-block path as __noinline__ functions: one rank's share of 8 0.154 vs 0.144 ms
 }
 
 
@@ -114,7 +116,7 @@ def build_variant(name, verbose=False):
     """libvxrt_exp_<name>.so: the library compiled with one experiment's macro (see VARIANTS)"""
     out = os.path.join(HERE, "libvxrt_exp_%s.so" % name)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + VARIANTS[name] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + dict(CLOSED_VARIANTS, **VARIANTS)[name] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
@@ -130,5 +132,5 @@ if __name__ == "__main__":
     print(build_hostlogic(force="--force" in sys.argv))
     print(build_glshim(force="--force" in sys.argv))
     for v in sys.argv[1:]:
-        if v in VARIANTS:
+        if v in VARIANTS or v in CLOSED_VARIANTS:
             print(build_variant(v))
