@@ -220,6 +220,10 @@ int vxrt_set_partition(vxrt_ctx* ctx, int mode);
    fshader.glsl:161-179), so the pixel is the same.  A small share of a frame lasts as long as its slowest block; this halves that
    block's sequential chain.  0 = off, default 8, at most 64.  Same pixels. */
 int vxrt_set_wide_tiles(vxrt_ctx* ctx, int tiles);
+/* The partition's arithmetic, host only (no device needed): the global tile (row-major, 32x8 pixels) that local tile `local_tile` of
+   `rank` renders, or -1 for padding; and the rank that owns global tile `tile`.  tile_rows as in vxrt_set_partition. */
+int vxrt_partition_tile(int width, int height, int rank, int world, int tile_rows, int local_tile);
+int vxrt_partition_owner(int width, int height, int world, int tile_rows, int tile);
 /* 1 when the last vxrt_render ran as one fused kernel (see vxrt_set_fusion), else 0. */
 int vxrt_frame_was_fused(vxrt_ctx* ctx);
 /* mode 0 (default) = the production kernels: no per-iteration counter, rays that cannot change a pixel are not traced

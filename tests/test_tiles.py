@@ -59,6 +59,37 @@ def test_tile_row_partition(vx, size, world):
         assert np.array_equal(t.assemble(gathered, w, h, rows=True), frame)
 
 
+@pytest.mark.parametrize("size", [(3840, 2160), (1920, 1080), (416, 236), (100, 37), (33, 9), (32, 8)])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("rows", [False, True], ids=["tiles", "tile_rows"])
+def test_library_partition_equals_the_host_statement(vx, size, world, rows):
+    """the library's own partition arithmetic (kernels.cuh tile_of / tile_owner, the table the render kernels read; exported host-only
+    as vxrt_partition_tile / vxrt_partition_owner) against tiles.py, for every local tile of every rank and every tile's owner"""
+    lib = vx.load_library()
+    t = vx.tiles
+    w, h = size
+    tx, ty, n = t.tile_counts(w, h)
+    nl = t.local_tiles(w, h, world, rows)
+    seen = []
+    for rank in range(world):
+        mine = [lib.vxrt_partition_tile(w, h, rank, world, int(rows), j) for j in range(nl)]
+        assert lib.vxrt_partition_tile(w, h, rank, world, int(rows), nl) == -1           # beyond the rank's local tiles
+        want = t.tiles_of_rank(w, h, rank, world, rows).tolist()
+        assert [g for g in mine if g >= 0] == want, (rank, mine[:8], want[:8])
+        if not (rows and world > 1):
+            # tile partition: local tile j is the rank's tile of group j (padding only in the last group)
+            assert all((g == -1) or (g // world == j) for j, g in enumerate(mine))
+        seen += [g for g in mine if g >= 0]
+    assert sorted(seen) == list(range(n))
+    step = max(1, n // 500)
+    tiles = list(range(0, n, step)) + [n - 1]
+    owner = t.pixel_owner(w, h, world, rows)
+    for g in tiles:
+        x0, y0 = (g % tx) * t.TILE_W, (g // tx) * t.TILE_H
+        assert lib.vxrt_partition_owner(w, h, world, int(rows), g) == int(owner[y0, x0]), g
+    assert lib.vxrt_partition_owner(w, h, world, int(rows), n) == -1
+
+
 def _gloo_worker(rank, world, port, level_path, tmpdir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

@@ -88,6 +88,8 @@ _SIGNATURES = {
     "vxrt_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_fusion": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_frame_was_fused": (C.c_int, [C.c_void_p]),
+    "vxrt_partition_tile": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "vxrt_partition_owner": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "vxrt_set_wide_tiles": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_partition": (C.c_int, [C.c_void_p, C.c_int]),
     "vxrt_set_stats": (C.c_int, [C.c_void_p, C.c_int]),

@@ -1266,6 +1266,21 @@ extern "C" int vxrt_set_wide_tiles(vxrt_ctx* c, int tiles) {
     return VXRT_OK;
 }
 
+// host-only: the partition's arithmetic (kernels.cuh tile_of / tile_owner) for tests and integrators; needs no device
+extern "C" int vxrt_partition_tile(int width, int height, int rank, int world, int tile_rows, int local_tile) {
+    if (width <= 0 || height <= 0 || world < 1 || rank < 0 || rank >= world || local_tile < 0) return -1;
+    const TileMap m = make_map(width, height, rank, world, tile_rows != 0);
+    if (local_tile >= m.nlocal) return -1;
+    const int t = tile_of(m, local_tile);
+    return t < m.ntiles ? t : -1;
+}
+extern "C" int vxrt_partition_owner(int width, int height, int world, int tile_rows, int tile) {
+    if (width <= 0 || height <= 0 || world < 1 || tile < 0) return -1;
+    const TileMap m = make_map(width, height, 0, world, tile_rows != 0);
+    if (tile >= m.ntiles) return -1;
+    return m.rows ? (tile / m.tx) % m.world : tile_owner(m, tile);
+}
+
 extern "C" int vxrt_frame_was_fused(vxrt_ctx* c) { return (c && c->last_fused) ? 1 : 0; }
 
 extern "C" int vxrt_set_overlap(vxrt_ctx* c, int mode) {
