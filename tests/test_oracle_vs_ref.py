@@ -42,6 +42,23 @@ def test_frames_bit_exact(oracle, ref_shader, default_level, name, size):
     assert float(steps.sum(dtype=np.float64)) == float(out["counters"][3])
 
 
+def test_overbright_clamp_light_sets_bit_exact(oracle, ref_shader, default_level):
+    """the light sets of tests/test_wide_oracle.py (clamp ending the loop in the first half / the second half / never, gaps between
+    the slots, the last active slot not slot 15, odd counts, negative / infinite / NaN weights) through the REFERENCE's shader:
+    what the early-out and the inactive slots do is pinned on the reference itself, not only on the restatement"""
+    import test_wide_oracle as two
+    W, H = 96, 54
+    aspect = np.float32(W) / np.float32(H)
+    for name, ls in two.light_sets().items():
+        fr = ol.make_frame(gc.CAM, aspect=aspect, lights=ls)
+        ref_shader.set_frame(fr)
+        rgba, _ = ref_shader.render(W, H)
+        out = oracle.render(default_level, gc.DIMS, fr, W, H, want_f32=True)["rgba_f32"]
+        same = rgba.view(np.uint32) == out.view(np.uint32)
+        both_nan = np.isnan(rgba) & np.isnan(out)
+        assert bool((same | both_nan).all()), (name, int((~(same | both_nan)).any(axis=2).sum()))
+
+
 def test_random_poses_bit_exact(oracle, ref_shader, default_level):
     rs = np.random.RandomState(5)
     rh = ol.RefHost()
